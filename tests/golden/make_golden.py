@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in ``tests/golden/`` FROM THE REFERENCE ITSELF.
+
+Runs only in the build container (needs ``/root/reference``): the reference's Python
+layers are imported by ``oracle/ref_loader.py`` (in-memory py3 patches, compiled
+``general`` module from the reference's own .pyx/.c), inputs are produced from fixed
+seeds, and inputs + reference outputs are stored as small ``.npz`` files.  The fixtures
+travel to the GPU box; the reference does not.
+
+    python tests/golden/make_golden.py            # regenerate everything (~2 min)
+
+Every array named ``ref_*`` is an output of the reference's code; everything else is input.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+warnings.filterwarnings("ignore")
+
+from oracle import build_ref, ref_loader  # noqa: E402
+
+DT_LONG = 1765.55929      # Kepler long cadence, scripts/flare_detection_efficiency.py:273
+DT_SHORT = 58.84876
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print("wrote %-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024.))
+
+
+def ref_flare(bf, ts, t0, amp, tg, te):
+    return bf.Flare(ts, amp=1.).model({"t0": t0, "amp": amp, "taugauss": tg, "tauexp": te})
+
+
+def gold_scalars(bf):
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.uniform(-50, 50, 40), [-np.inf, -np.inf, 0., 3., np.inf]])
+    ys = np.concatenate([rng.uniform(-50, 50, 40), [-np.inf, 2., -np.inf, 3., 1.]])
+    lp = np.array([bf.logplus(x, y) for x, y in zip(xs, ys)])
+    lm = np.array([bf.logminus(x, y) for x, y in zip(xs, ys)])
+    lts_in, lts_t, lts_out = [], [], []
+    for n in (2, 3, 5, 10, 17):
+        t = np.sort(rng.uniform(0, 100, n))
+        lx = rng.uniform(-30, 30, n)
+        if n == 5:
+            lx[1] = -np.inf
+        if n == 10:
+            lx[:] = -np.inf
+        lts_in.append(lx), lts_t.append(t), lts_out.append(bf.logtrapz(lx, t))
+    save("scalars", x=xs, y=ys, ref_logplus=lp, ref_logminus=lm,
+         lt_sizes=np.array([len(a) for a in lts_in]), lt_lx=np.concatenate(lts_in), lt_t=np.concatenate(lts_t),
+         ref_logtrapz=np.array(lts_out),
+         kat_logplus_1_2=np.array(bf.logplus(1, 2)),
+         kat_logtrapz=np.array(bf.logtrapz(np.array([0, -1, -np.inf]), np.array([0., 1, 2]))))
+
+
+def gold_elimination():
+    """log_marg_amp_full_C / log_marg_amp_except_final_C called directly through ctypes on
+    the reference's own compiled C (oracle/_ref/liblogmarg.so)."""
+    built = build_ref.build()
+    L = C.CDLL(built["liblogmarg"])
+    dp = C.POINTER(C.c_double)
+    L.log_marg_amp_full_C.restype = C.c_double
+    L.log_marg_amp_full_C.argtypes = [C.c_int, dp, dp, C.c_double, C.c_uint]
+    L.log_marg_amp_except_final_C.restype = C.c_double
+    L.log_marg_amp_except_final_C.argtypes = [C.c_int, dp, dp, C.c_double]
+    rng = np.random.default_rng(7)
+    NM = 8
+    n = 400
+    Ms = np.zeros((n, NM, NM))
+    Ds = np.zeros((n, NM))
+    nms = np.zeros(n, dtype=np.int32)
+    sig = np.zeros(n)
+    out = np.zeros((n, 3))
+    for t in range(n):
+        nm = int(rng.integers(2, NM + 1))
+        A = rng.standard_normal((nm + 3, nm))
+        if t % 5 == 0:   # Hilbert-like, as the monomial Gram matrices on the path are
+            x = np.linspace(0, 1, 55)
+            A = np.array([x ** p for p in range(nm - 1)] + [np.exp(-x * rng.uniform(1, 20))]).T
+        M = np.triu(A.T @ A)
+        D = rng.standard_normal(nm) * rng.uniform(0.1, 30)
+        if t % 5 == 0:
+            D = A.T @ (rng.standard_normal(55) + 3 * A[:, -1])
+        s = 1.0 if t % 2 else rng.uniform(0.5, 2)
+        if t == 17:
+            D[1] = np.inf
+        if t == 18:
+            M[0, 0] = np.nan
+        Mc = np.ascontiguousarray(M)
+        nms[t], sig[t] = nm, s
+        Ms[t, :nm, :nm], Ds[t, :nm] = M, D
+        out[t, 0] = L.log_marg_amp_full_C(nm, Mc.ctypes.data_as(dp), D.ctypes.data_as(dp), s, 0)
+        out[t, 1] = L.log_marg_amp_full_C(nm, Mc.ctypes.data_as(dp), D.ctypes.data_as(dp), s, 1)
+        out[t, 2] = L.log_marg_amp_except_final_C(nm, Mc.ctypes.data_as(dp), D.ctypes.data_as(dp), s)
+    save("elimination", M=Ms, D=Ds, nm=nms, sigma=sig, ref_full_lhr0=out[:, 0], ref_full_lhr1=out[:, 1],
+         ref_except_final=out[:, 2])
+
+
+def _force_sk(sk):
+    import bayesflare.stats.bayes as bb
+    orig = bb.estimate_noise_ps
+    bb.estimate_noise_ps = lambda lc, estfrac=0.5: (sk, sk * sk, None)
+    return bb, orig
+
+
+def gold_kat200(bf):
+    """Deterministic N=200 curve with *varying* per-sample errors (general-variance path),
+    noise sigma forced to 0.9 so the fixture is independent of the noise estimator.
+    Every hypothesis type, all samples including the truncated-window edges."""
+    N = 200
+    i = np.arange(N)
+    clc = np.sin(0.37 * i) + 0.5 * np.cos(0.011 * i ** 2) + 3 * np.exp(-np.maximum(i - 100, 0) / 2.) * (i >= 100)
+    cle = 0.1 + 0.05 * np.sin(0.05 * i) ** 2
+    ts = i * DT_LONG
+    lc = ref_loader.RefLightcurve(ts, clc, cle)
+    bb, orig = _force_sk(0.9)
+    out = dict(cts=ts, clc=clc, cle=cle, sk=np.array(0.9))
+    try:
+        dt = ts[1] - ts[0]
+        cases = {
+            "flare": (bf.Flare, {}, {"t0": (np.inf,), "taugauss": (0, 5400, 4), "tauexp": (1800, 10800, 4), "amp": (1.,)}, True),
+            "impulse": (bf.Impulse, {}, {"t0": (0, 54 * dt, 55), "amp": (1.,)}, False),
+            "impulse1": (bf.Impulse, {}, {"t0": (np.inf,), "amp": (1.,)}, False),
+            "expdecay": (bf.Expdecay, {}, {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True),
+            "expdecay_rev": (bf.Expdecay, {"reverse": True}, {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True),
+            "step": (bf.Step, {}, {"t0": (np.inf,), "amp": (1.,)}, False),
+            "transit": (bf.Transit, {}, {"t0": (np.inf,), "sigmag": (1800, 7200, 3), "tauf": (0, 7200, 4), "amp": (1.,)}, True),
+            "flare_full": (bf.Flare, {}, {"t0": (np.inf,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3), "amp": (1.,)}, False),
+        }
+        for name, (cls, kw, pr, hr) in cases.items():
+            M = cls(lc.cts, amp=1, paramranges=dict(pr), **kw)
+            B = bf.Bayes(lc, M)
+            B.bayes_factors_marg_poly_bgd(halfrange=hr)
+            out["ref_lnB_" + name] = B.lnBmargAmp
+            out["ref_marg_" + name] = B.marginalise_full().lnBmargAmp
+            if name == "flare":
+                out["ref_bgonly"] = B.bayes_factors_marg_poly_bgd_only()
+                out["ref_noise_ev"] = np.array(B.noise_ev)
+        # a different window / polynomial order
+        M = bf.Flare(lc.cts, amp=1, paramranges=dict(cases["flare"][2]))
+        B = bf.Bayes(lc, M)
+        B.bayes_factors_marg_poly_bgd(bglen=21, bgorder=2)
+        out["ref_lnB_flare_w21_o2"] = B.lnBmargAmp
+        out["ref_bgonly_w21_o2"] = B.bayes_factors_marg_poly_bgd_only(bglen=21, bgorder=2)
+    finally:
+        bb.estimate_noise_ps = orig
+    save("kat200", **out)
+
+
+def sim_curve(bf, N, seed, dt=DT_LONG, flares=(), sinamp=0.0, nstd=1.0):
+    rng = np.random.RandomState(seed)
+    ts = np.arange(N) * dt
+    clc = nstd * rng.randn(N)
+    if sinamp:
+        clc = clc + sinamp * np.sin(2 * np.pi * ts / (3.3 * 86400.) + 0.7)
+    for (idx, amp, tg, te) in flares:
+        clc = clc + ref_flare(bf, ts, ts[idx], amp, tg, te)
+    clc = clc - np.median(clc)      # Lightcurve.dcoffset, data/data.py:271-277
+    return ts, clc
+
+
+def gold_detector(bf):
+    out = {}
+    # (a) N=1000, both noise estimators, default detector
+    ts, clc = sim_curve(bf, 1000, 101, flares=[(400, 12., 1000., 3000.), (700, 6., 500., 6000.)], sinamp=2.0)
+    lc = ref_loader.RefLightcurve(ts, clc)
+    out.update(a_cts=ts, a_clc=clc)
+    for meth in ("powerspectrum", "tailveto"):
+        det = bf.OddsRatioDetector(lc, noiseestmethod=meth)
+        lnO, tso = det.oddsratio()
+        out["ref_a_lnO_" + meth] = np.array(lnO)
+        fl, nfl, mx = det.thresholder(lnO, 16.5, expand=1)
+        out["ref_a_segs_" + meth] = np.array(fl, dtype=np.int64).reshape(-1, 2)
+        out["ref_a_max_" + meth] = np.array(mx, dtype=float).reshape(-1, 2)
+    # noise sigma as the reference computes it (bayes.py:235-246)
+    from copy import deepcopy
+    tmp = deepcopy(lc)
+    tmp.detrend(method="savitzkygolay", nbins=55, order=4)
+    out["ref_a_sk_ps"] = np.array(bf.estimate_noise_ps(tmp, estfrac=0.5)[0])
+    out["ref_a_sk_tv"] = np.array(bf.estimate_noise_tv(tmp.clc, sigma=1.0)[0])
+    out["ref_a_sgfit"] = bf.savitzky_golay(lc.clc, 55, 4)
+    # (b) the scripts' detector (55-point impulse grid, tailveto), N=1639
+    # scripts/flare_detection_efficiency.py:495-507
+    N = int(np.ceil(2893536. / DT_LONG))
+    ts, clc = sim_curve(bf, N, 202, flares=[(800, 9., 2000., 4000.)])
+    lc = ref_loader.RefLightcurve(ts, clc)
+    det = bf.OddsRatioDetector(lc, bglen=55, bgorder=4, noiseestmethod="tailveto", tvsigma=1.0,
+                               flareparams={"taugauss": (0, 1.5 * 3600, 10), "tauexp": (0.5 * 3600, 3 * 3600, 10)},
+                               noisepoly=True, noiseimpulse=True,
+                               noiseimpulseparams={"t0": (0, 54 * DT_LONG, 55)},
+                               noiseexpdecay=True, noiseexpdecayparams={"tauexp": (0.0, 0.25 * 3600, 3)},
+                               noiseexpdecaywithreverse=True, ignoreedges=True)
+    lnO, tso = det.oddsratio()
+    out.update(b_cts=ts, b_clc=clc, ref_b_lnO=np.array(lnO))
+    fl, nfl, mx = det.thresholder(lnO, 10.0, expand=2)
+    out["ref_b_segs"] = np.array(fl, dtype=np.int64).reshape(-1, 2)
+    out["ref_b_max"] = np.array(mx, dtype=float).reshape(-1, 2)
+    # (c) step hypothesis on, edges kept, positive impulse
+    ts, clc = sim_curve(bf, 400, 303, flares=[(200, 10., 800., 2500.)])
+    lc = ref_loader.RefLightcurve(ts, clc)
+    det = bf.OddsRatioDetector(lc, noiseestmethod="tailveto", noisestep=True, ignoreedges=False)
+    det.set_noise_impulse(noiseimpulse=True, noiseimpulseparams={"t0": (np.inf,)}, positive=True)
+    lnO, tso = det.oddsratio()
+    out.update(c_cts=ts, c_clc=clc, ref_c_lnO=np.array(lnO))
+    save("detector", **out)
+
+
+def gold_config1(bf):
+    """BASELINE config 1 shape: N=4400, default detector; the SURVEY 8(c) end-to-end KAT."""
+    np.random.seed(1)
+    N = 4400
+    ts = np.arange(N) * DT_LONG
+    clc = np.random.randn(N) + ref_flare(bf, ts, ts[2200], 8., 1000., 3000.)
+    lc = ref_loader.RefLightcurve(ts, clc)
+    out = dict(cts=ts, clc=clc)
+    for meth in ("powerspectrum", "tailveto"):
+        det = bf.OddsRatioDetector(lc, noiseestmethod=meth)
+        lnO, tso = det.oddsratio()
+        out["ref_lnO_" + meth] = np.array(lnO)
+        fl, nfl, mx = det.thresholder(lnO, 16.5, expand=1)
+        out["ref_segs_" + meth] = np.array(fl, dtype=np.int64).reshape(-1, 2)
+        out["ref_max_" + meth] = np.array(mx, dtype=float).reshape(-1, 2)
+        print(meth, "max lnO", np.max(lnO), int(np.argmax(lnO)), fl)
+    save("config1", **out)
+
+
+def gold_short_cadence(bf):
+    """BASELINE config 2 shape at reduced length: short cadence (58.8 s), N=6000."""
+    ts, clc = sim_curve(bf, 6000, 404, dt=DT_SHORT, flares=[(2500, 6., 300., 1500.), (4000, 15., 100., 600.)])
+    lc = ref_loader.RefLightcurve(ts, clc)
+    det = bf.OddsRatioDetector(lc, noiseestmethod="powerspectrum")
+    lnO, tso = det.oddsratio()
+    save("shortcad", cts=ts, clc=clc, ref_lnO=np.array(lnO))
+
+
+def gold_pe(bf):
+    """BASELINE config 4 (reduced grid): scripts/parameter_estimation_example.py:27-64."""
+    rng = np.random.RandomState(505)
+    ts = np.arange(0., 2893536., DT_LONG, dtype="float64")
+    clc = rng.randn(len(ts))
+    t0, amp, taug, taue = 400000., 20.0, 1060.0, 2168.0
+    clc = clc + ref_flare(bf, ts, t0, amp, taug, taue)
+    lc = ref_loader.RefLightcurve(ts, clc)
+    idxt0 = int(t0 / lc.dt())
+    out = dict(cts=ts, clc=clc, t0=np.array(t0), idxt0=np.array(idxt0))
+    for bgorder in (3, 4, 2):
+        pe = bf.ParameterEstimationGrid("flare", lc)
+        pe.lightcurve_chunk(idxt0, 55)
+        amprange = (0., 1.6 * (np.amax(pe.lightcurve.clc) - np.amin(pe.lightcurve.clc)), 9)
+        pe.set_grid(ranges={"taugauss": (0., 3600., 12), "tauexp": (0., 12000., 10), "amp": amprange, "t0": (t0,)})
+        pe.calculate_posterior(bgorder=bgorder)
+        out["ref_sigma"] = np.array(pe.noiseSigma)
+        out["amprange"] = np.array(amprange)
+        out["ref_post_o%d" % bgorder] = pe.posterior
+        if bgorder == 3:
+            pe.marginalise_all()
+            for p in ("taugauss", "tauexp", "amp"):
+                out["ref_margpost_" + p] = pe.margposteriors[p]
+            mp, mpar = pe.maximum_posterior()
+            out["ref_maxpost"] = np.array(mp)
+            out["ref_maxpost_params"] = np.array([mpar[p] for p in ("t0", "tauexp", "taugauss", "amp")], dtype=float)
+            out["ref_snr"] = np.array(pe.maximum_posterior_snr())
+    pe = bf.ParameterEstimationGrid("flare", lc)
+    pe.lightcurve_chunk(idxt0, 55)
+    pe.set_grid(ranges={"taugauss": (0., 3600., 6), "tauexp": (0., 12000., 5), "amp": amprange, "t0": (t0,)})
+    pe.calculate_posterior(margbackground=False)
+    out["ref_post_nobg"] = pe.posterior
+    save("pegrid", **out)
+
+
+def main():
+    bf = ref_loader.load_reference()
+    which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid"]
+    if "scalars" in which:
+        gold_scalars(bf)
+    if "elimination" in which:
+        gold_elimination()
+    if "kat200" in which:
+        gold_kat200(bf)
+    if "detector" in which:
+        gold_detector(bf)
+    if "pegrid" in which:
+        gold_pe(bf)
+    if "shortcad" in which:
+        gold_short_cadence(bf)
+    if "config1" in which:
+        gold_config1(bf)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,138 @@
+"""CPU: the oracle restatement (oracle/) against the golden fixtures generated from the
+reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import assert_logodds_close, load_golden
+from oracle import oracle as orc
+
+DT = 1765.55929
+
+
+def test_scalars():
+    g = load_golden("scalars")
+    got = np.array([orc.logplus(x, y) for x, y in zip(g["x"], g["y"])])
+    np.testing.assert_array_equal(got, g["ref_logplus"])
+    assert orc.logplus(1, 2) == float(g["kat_logplus_1_2"]) == 2.313261687518223
+    off = 0
+    for n, ref in zip(g["lt_sizes"], g["ref_logtrapz"]):
+        lx, t = g["lt_lx"][off:off + n], g["lt_t"][off:off + n]
+        off += n
+        got = orc.logtrapz(lx, t)
+        assert got == ref or abs(got - ref) <= 1e-15 * abs(ref)
+    assert orc.logtrapz([0, -1, -np.inf], [0., 1, 2]) == -0.14170246662789426
+
+
+def test_elimination_bit_exact():
+    g = load_golden("elimination")
+    for t in range(len(g["nm"])):
+        nm = int(g["nm"][t])
+        M = np.ascontiguousarray(g["M"][t, :nm, :nm])
+        D = np.ascontiguousarray(g["D"][t, :nm])
+        s = float(g["sigma"][t])
+        for lhr, key in ((0, "ref_full_lhr0"), (1, "ref_full_lhr1")):
+            got, ref = orc.marg_full(M, D, s, lhr), g[key][t]
+            assert got == ref or (np.isnan(got) and np.isnan(ref)), (t, lhr, got, ref)
+        got, ref = orc.marg_except_final(M, D, s), g["ref_except_final"][t]
+        assert got == ref or (np.isnan(got) and np.isnan(ref)), (t, got, ref)
+
+
+def test_pairwise_sum_is_numpy_order():
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 140)) + [200, 1000, 4400]:
+        a = rng.standard_normal(n) * 10 ** rng.uniform(-3, 3, n)
+        assert orc.pairwise_sum(a) == np.sum(a)
+
+
+KAT_CASES = {
+    "flare": ("flare", {"t0": (np.inf,), "taugauss": (0, 5400, 4), "tauexp": (1800, 10800, 4), "amp": (1.,)}, True, False),
+    "impulse": ("impulse", {"t0": (0, 54 * DT, 55), "amp": (1.,)}, False, False),
+    "impulse1": ("impulse", {"t0": (np.inf,), "amp": (1.,)}, False, False),
+    "expdecay": ("expdecay", {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True, False),
+    "expdecay_rev": ("expdecay", {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True, True),
+    "step": ("step", {"t0": (np.inf,), "amp": (1.,)}, False, False),
+    "transit": ("transit", {"t0": (np.inf,), "sigmag": (1800, 7200, 3), "tauf": (0, 7200, 4), "amp": (1.,)}, True, False),
+    "flare_full": ("flare", {"t0": (np.inf,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3), "amp": (1.,)}, False, False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(KAT_CASES))
+def test_kat200_bayes_factors(name):
+    g = load_golden("kat200")
+    mtype, pr, hr, rev = KAT_CASES[name]
+    lnB, ranges = orc.bayes_factors(g["clc"], g["cle"], g["cts"], mtype, pr, float(g["sk"]), halfrange=hr, reverse=rev)
+    assert_logodds_close(lnB, g["ref_lnB_" + name], 1e-9, name)
+    marg = orc.marginalise_full(lnB, ranges, orc.MODEL_PARAMNAMES[mtype])
+    assert_logodds_close(marg, g["ref_marg_" + name], 1e-9, name + " marg")
+
+
+def test_kat200_background_and_window():
+    g = load_golden("kat200")
+    bgo = orc.background_only(g["clc"], g["cle"], g["cts"], float(g["sk"]))
+    assert_logodds_close(bgo, g["ref_bgonly"], 1e-9, "bgonly")
+    pr = KAT_CASES["flare"][1]
+    lnB, _, bg2 = orc.bayes_factors(g["clc"], g["cle"], g["cts"], "flare", pr, float(g["sk"]), bglen=21, bgorder=2,
+                                    with_background=True)
+    assert_logodds_close(lnB, g["ref_lnB_flare_w21_o2"], 1e-9, "w21")
+    assert_logodds_close(bg2, g["ref_bgonly_w21_o2"], 1e-9, "w21 bg")
+    # SURVEY.md 8(c) known answers
+    lnB, ranges = orc.bayes_factors(g["clc"], g["cle"], g["cts"], "flare", pr, 0.9)
+    assert abs(lnB[0, 3, 0, 0, 100] - (-19.112936560497506)) < 1e-11
+    marg = orc.marginalise_full(lnB, ranges, orc.MODEL_PARAMNAMES["flare"])
+    assert abs(marg[100] - (-3.7608624961601813)) < 1e-11
+
+
+def test_noise_estimators():
+    g = load_golden("detector")
+    clc, cts = g["a_clc"], g["a_cts"]
+    np.testing.assert_allclose(orc.savitzky_golay(clc, 55, 4), g["ref_a_sgfit"], rtol=0, atol=1e-12)
+    assert abs(orc.noise_sigma(clc, cts, 55, 4, "powerspectrum") - float(g["ref_a_sk_ps"])) < 1e-13
+    assert abs(orc.noise_sigma(clc, cts, 55, 4, "tailveto") - float(g["ref_a_sk_tv"])) < 1e-13
+
+
+@pytest.mark.parametrize("meth", ["powerspectrum", "tailveto"])
+def test_detector_default(meth):
+    g = load_golden("detector")
+    lnO, ts = orc.oddsratio(g["a_clc"], np.zeros_like(g["a_clc"]), g["a_cts"], noiseestmethod=meth)
+    assert_logodds_close(lnO, g["ref_a_lnO_" + meth], 1e-9, meth)
+    segs, n, mx = orc.thresholder(lnO, 16.5, expand=1)
+    assert np.array_equal(np.array(segs, dtype=np.int64).reshape(-1, 2), g["ref_a_segs_" + meth])
+    assert np.array_equal(np.array([m[1] for m in mx], dtype=float), g["ref_a_max_" + meth][:, 1])
+
+
+def test_detector_scripts_config_and_options():
+    g = load_golden("detector")
+    lnO, ts = orc.oddsratio(g["b_clc"], np.zeros_like(g["b_clc"]), g["b_cts"], noiseestmethod="tailveto",
+                            noiseimpulseparams={"t0": (0, 54 * DT, 55)})
+    assert_logodds_close(lnO, g["ref_b_lnO"], 1e-9, "scripts detector")
+    segs, n, mx = orc.thresholder(lnO, 10.0, expand=2)
+    assert np.array_equal(np.array(segs, dtype=np.int64).reshape(-1, 2), g["ref_b_segs"])
+    lnO, ts = orc.oddsratio(g["c_clc"], np.zeros_like(g["c_clc"]), g["c_cts"], noiseestmethod="tailveto",
+                            noisestep=True, ignoreedges=False, noiseimpulsepositive=True)
+    assert_logodds_close(lnO, g["ref_c_lnO"], 1e-9, "step+edges")
+
+
+def test_config1_end_to_end_kat():
+    g = load_golden("config1")
+    lnO, ts = orc.oddsratio(g["clc"], np.zeros_like(g["clc"]), g["cts"], noiseestmethod="powerspectrum")
+    assert_logodds_close(lnO, g["ref_lnO_powerspectrum"], 1e-9, "config1")
+    assert len(lnO) == 4346 and int(np.argmax(lnO)) == 2174
+    assert abs(np.max(lnO) - 18.343102610670442) < 1e-10
+    segs, n, mx = orc.thresholder(lnO, 16.5, expand=1)
+    assert [tuple(s) for s in segs] == [(2171, 2176)]
+
+
+def test_pe_grid():
+    g = load_golden("pegrid")
+    cts, clc, t0, idx = g["cts"], g["clc"], float(g["t0"]), int(g["idxt0"])
+    s, e = idx - 27, idx + 28
+    a = g["amprange"]
+    for bgorder in (2, 3, 4):
+        grid = {"t0": np.array([t0], dtype="float32"), "tauexp": np.linspace(0., 12000., 10),
+                "taugauss": np.linspace(0., 3600., 12), "amp": np.linspace(a[0], a[1], int(a[2]))}
+        post = orc.pe_posterior(clc[s:e], cts[s:e], "flare", grid, float(g["ref_sigma"]), bgorder=bgorder)
+        assert_logodds_close(post, g["ref_post_o%d" % bgorder], 1e-9, "pe o%d" % bgorder)
+    grid = {"t0": np.array([t0], dtype="float32"), "tauexp": np.linspace(0., 12000., 5),
+            "taugauss": np.linspace(0., 3600., 6), "amp": np.linspace(a[0], a[1], int(a[2]))}
+    post = orc.pe_posterior(clc[s:e], cts[s:e], "flare", grid, float(g["ref_sigma"]), margbackground=False)
+    assert_logodds_close(post, g["ref_post_nobg"], 1e-9, "pe nobg")
