@@ -1,0 +1,261 @@
+"""ctypes binding of ``libbfl.so`` (C ABI declared in ``include/bfl.h``).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present when a
+compute entry point is called, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbfl.so")
+
+MODEL_KINDS = {"flare": 0, "expdecay": 1, "impulse": 2, "step": 3, "transit": 4, "gaussian": 5, "table": 6}
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+class BflError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbfl error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Hypothesis(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reverse", C.c_int32), ("halfrange", C.c_int32), ("ngrid", C.c_int32),
+                ("params", _dp), ("logprior", _dp), ("logweight", _dp), ("table", _dp)]
+
+
+# every symbol include/bfl.h declares: (restype, argtypes)
+SIGNATURES = {
+    "bfl_version": (C.c_int, []),
+    "bfl_last_error": (C.c_char_p, []),
+    "bfl_device_count": (C.c_int, []),
+    "bfl_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bfl_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "bfl_ctx_sync": (C.c_int, [C.c_void_p]),
+    "bfl_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "bfl_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(Hypothesis), C.c_int,
+                                  C.POINTER(C.c_void_p)]),
+    "bfl_plan_destroy": (C.c_int, [C.c_void_p]),
+    "bfl_plan_templates": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "bfl_window_lnB": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int64, C.c_double,
+                                 _dp, _dp]),
+    "bfl_detector_odds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int32, C.c_int64, _dp, _dp]),
+    "bfl_detector_odds_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                        C.c_int64, C.c_void_p]),
+    "bfl_threshold": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_double, C.c_int32, _i64p, _dp, _i64p, C.c_int32,
+                                C.POINTER(C.c_int32)]),
+    "bfl_pe_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, C.c_int64, C.c_int32,
+                              _dp, C.c_double, C.c_int32, _dp]),
+    "bfl_logtrapz": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64, _dp]),
+    "bfl_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libbfl.so and declare every prototype.  Raises if the library is not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError("%s is not built (run `python -m bayesflare_b200.build`); "
+                                  "bayesflare_b200 has no CPU fallback" % LIB_PATH)
+            L = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise BflError(rc, (load().bfl_last_error() or b"").decode("utf-8", "replace"))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Context:
+    """One device + one stream + grow-only scratch (``bfl_ctx``)."""
+
+    def __init__(self, device=-1, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.bfl_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+
+    def sync(self):
+        check(self.lib.bfl_ctx_sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(self.lib.bfl_ctx_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bfl_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide context for ``device`` (default: ``BFL_DEVICE`` or LOCAL_RANK or 0)."""
+    if device is None:
+        device = int(os.environ.get("BFL_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        ndev = load().bfl_device_count()
+        if ndev > 0:
+            device %= ndev
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+class Plan:
+    """``bfl_plan``: hypotheses (templates + per-grid constants) on one window time base."""
+
+    def __init__(self, ctx, bglen, bgmodels, mts, hyps):
+        """hyps: list of dicts(kind, reverse, halfrange, params[G,4], logprior[G], logweight[G], table)."""
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.bglen = int(bglen)
+        bg = f64(bgmodels)
+        self.npoly = bg.shape[0]
+        keep = [bg, f64(mts)]
+        arr = (Hypothesis * max(len(hyps), 1))()
+        self.ngrid = []
+        for i, h in enumerate(hyps):
+            lp, lw = f64(h["logprior"]).ravel(), f64(h["logweight"]).ravel()
+            G = lp.size
+            par = f64(h["params"]).reshape(G, 4) if h.get("params") is not None else None
+            tab = f64(h["table"]).reshape(G, self.bglen) if h.get("table") is not None else None
+            keep += [lp, lw, par, tab]
+            arr[i].kind = MODEL_KINDS[h["kind"]] if isinstance(h["kind"], str) else int(h["kind"])
+            arr[i].reverse = 1 if h.get("reverse") else 0
+            arr[i].halfrange = 1 if h.get("halfrange") else 0
+            arr[i].ngrid = G
+            arr[i].params = ptr(par)
+            arr[i].logprior = ptr(lp)
+            arr[i].logweight = ptr(lw)
+            arr[i].table = ptr(tab)
+            self.ngrid.append(G)
+        self.nhyp = len(hyps)
+        hnd = C.c_void_p()
+        check(self.lib.bfl_plan_create(ctx.handle, self.bglen, self.npoly, ptr(bg), ptr(keep[1]), arr, self.nhyp,
+                                       C.byref(hnd)))
+        self.handle = hnd
+
+    def templates(self, ihyp):
+        out = np.zeros((self.ngrid[ihyp], self.bglen))
+        check(self.lib.bfl_plan_templates(self.handle, int(ihyp), ptr(out)))
+        return out
+
+    def window_lnB(self, ihyp, clc, cle, sk, sumlogsigma, want_lnB=True, want_bg=False):
+        clc = f64(clc)
+        cle = None if cle is None else f64(cle)
+        N = clc.size
+        out = np.empty((self.ngrid[ihyp], N)) if want_lnB else None
+        bg = np.empty(N) if want_bg else None
+        check(self.lib.bfl_window_lnB(self.ctx.handle, self.handle, int(ihyp) if want_lnB else -1, ptr(clc), ptr(cle),
+                                      float(sk), N, float(sumlogsigma), ptr(out), ptr(bg)))
+        return out, bg
+
+    def detector_odds(self, clc, cle, sk, noisepoly=True, want_marg=False):
+        clc = f64(clc)
+        single = clc.ndim == 1
+        clc = np.atleast_2d(clc)
+        B, N = clc.shape
+        cle = None if cle is None else np.atleast_2d(f64(cle))
+        sk = f64(np.atleast_1d(sk))
+        if sk.size != B or (cle is not None and cle.shape != clc.shape):
+            raise ValueError("batch shapes of clc, cle and sk do not agree")
+        lnO = np.empty((B, N))
+        marg = np.empty((self.nhyp + 1, B, N)) if want_marg else None
+        check(self.lib.bfl_detector_odds(self.ctx.handle, self.handle, 1 if noisepoly else 0, ptr(clc), ptr(cle),
+                                         ptr(sk), B, N, ptr(lnO), ptr(marg)))
+        if single:
+            lnO = lnO[0]
+            marg = None if marg is None else marg[:, 0]
+        return (lnO, marg) if want_marg else lnO
+
+    def detector_odds_dev(self, d_clc, d_cle, const_var, d_sk, B, N, seg0, seglen, k0, k1, d_lnO, noisepoly=True):
+        """Device-resident, asynchronous variant: arguments are raw device addresses (ints)."""
+        check(self.lib.bfl_detector_odds_dev(self.ctx.handle, self.handle, 1 if noisepoly else 0, d_clc, d_cle or None,
+                                             1 if const_var else 0, d_sk, int(B), int(N), int(seg0), int(seglen),
+                                             int(k0), int(k1), d_lnO))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bfl_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def threshold(ctx, lnO, thresh, expand=0):
+    lnO = f64(lnO)
+    n = lnO.size
+    cap = max(16, n // 2 + 2)
+    segs = np.zeros((cap, 2), dtype=np.int64)
+    mv = np.zeros(cap)
+    mi = np.zeros(cap, dtype=np.int64)
+    ns = C.c_int32(0)
+    check(ctx.lib.bfl_threshold(ctx.handle, ptr(lnO), n, float(thresh), int(expand), segs.ctypes.data_as(_i64p),
+                                ptr(mv), mi.ctypes.data_as(_i64p), cap, C.byref(ns)))
+    k = ns.value
+    return segs[:k], mv[:k], mi[:k]
+
+
+def pe_grid(ctx, kind, reverse, cts, clc, params, logprior, npoly, polyms, sigma, margbackground):
+    cts, clc, params, logprior = f64(cts), f64(clc), f64(params), f64(logprior)
+    G = logprior.size
+    polyms = None if polyms is None else f64(polyms)
+    out = np.empty(G)
+    check(ctx.lib.bfl_pe_grid(ctx.handle, MODEL_KINDS[kind], 1 if reverse else 0, ptr(cts), ptr(clc), cts.size,
+                              ptr(params), ptr(logprior), G, int(npoly), ptr(polyms), float(sigma),
+                              1 if margbackground else 0, ptr(out)))
+    return out
+
+
+def logtrapz_axis0(ctx, lx, t):
+    lx, t = f64(lx), f64(t)
+    n = lx.shape[0]
+    m = int(np.prod(lx.shape[1:])) if lx.ndim > 1 else 1
+    out = np.empty(m)
+    check(ctx.lib.bfl_logtrapz(ctx.handle, ptr(lx), ptr(t), n, m, ptr(out)))
+    return out.reshape(lx.shape[1:])
+
+
+def fp64_peak(ctx, iters=4096):
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(ctx.lib.bfl_fp64_peak_probe(ctx.handle, int(iters), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value

@@ -1,0 +1,423 @@
+"""``Bayes`` and ``ParameterEstimationGrid`` -- drop-in mirrors of ``bayesflare/stats/bayes.py``
+whose numerical work is done by ``libbfl`` on the GPU.
+
+Host side (this file): argument checking, the scalar noise estimate, the window time stamps,
+grid axes, priors and trapezium weights.  Device side: templates, every cross term, the
+amplitude marginalisation for every (sample, grid point), the grid marginalisation.
+"""
+from __future__ import annotations
+
+from copy import copy, deepcopy
+from math import pi
+
+import numpy as np
+
+from . import _lib
+from .general import logtrapz
+from .noise import estimate_noise_ps, estimate_noise_tv
+
+__all__ = ["Bayes", "ParameterEstimationGrid", "window_times", "background_models", "estimate_sigma",
+           "hypothesis_from_model"]
+
+
+# ---- host-side pieces of bayes_factors_marg_poly_bgd shared with the detector ------------
+def window_times(ts, bglen, model_t0):
+    """The ``bglen`` time stamps the templates are evaluated on (bayes.py:261-276)."""
+    N = len(ts)
+    nsteps = int(bglen / 2)
+    dt = ts[1] - ts[0]
+    idxt0 = int((model_t0 - ts[0]) / dt) + 1
+    idx1, idx2 = idxt0 - nsteps, idxt0 + nsteps + 1
+    if idx1 < 0:
+        return ts[:bglen]
+    if idx2 > N - 1:
+        return ts[-bglen:]
+    return ts[idx1:idx2]
+
+
+def background_models(bglen, bgorder):
+    """Monomials on [0, 1] (bayes.py:292-307), computed by NumPy exactly as the reference does."""
+    tsp = np.linspace(0., 1., bglen)
+    return np.array([tsp ** i for i in range(bgorder + 1)])
+
+
+def estimate_sigma(lightcurve, bglen, bgorder, noiseestmethod, psestfrac, tvsigma):
+    """Noise sigma on a Savitzky-Golay detrended copy (bayes.py:235-246).  Returns ``None`` for
+    an unknown method, after printing the reference's message."""
+    tmpcurve = deepcopy(lightcurve)
+    if tmpcurve.detrended is False:
+        tmpcurve.detrend(method='savitzkygolay', nbins=bglen, order=bgorder)
+    if noiseestmethod == 'powerspectrum':
+        return estimate_noise_ps(tmpcurve, estfrac=psestfrac)[0]
+    if noiseestmethod == 'tailveto':
+        return estimate_noise_tv(tmpcurve.clc, sigma=tvsigma)[0]
+    print("Noise estimation method must be 'powerspectrum' or 'tailveto'")
+    return None
+
+
+def hypothesis_from_model(model, mts, halfrange, ranges=None):
+    """Describe ``model``'s parameter grid for ``libbfl`` (``bfl_hypothesis`` in include/bfl.h)."""
+    if ranges is not None:
+        model = copy(model)
+        model.ranges = ranges
+    logprior = model.grid_logprior() + (np.log(0.5) if halfrange else 0.)    # bayes.py:284-288
+    h = dict(kind=model.device_kind or "table", reverse=bool(model.reverse), halfrange=bool(halfrange),
+             params=model.grid_params(), logprior=logprior, logweight=model.grid_logweight(), table=None)
+    if model.device_kind is None:
+        # a user-defined Model subclass: evaluate its templates on the host, upload as a table
+        G = int(np.prod(model.shape))
+        tab = np.zeros((G, len(mts)))
+        for q in range(G):
+            if np.isfinite(logprior[q]):
+                tab[q] = model(q, ts=mts, filt=False).clc
+        h["table"] = tab
+    return h
+
+
+def _sumlogsigma(noisevar):
+    sk = np.sqrt(noisevar)                      # bayes.py:419
+    return float(np.sum(np.log(sk[np.isfinite(sk)])))   # general.pyx:216-221
+
+
+class Bayes:
+    """Bayesian odds ratios of a model against Gaussian noise for every sample of a light curve
+    (bayes.py:76-639).
+
+    Parameters
+    ----------
+    lightcurve : Lightcurve-like (``cts, clc, cle, detrended, detrend()``)
+    model : a :class:`Model` with a parameter grid
+    """
+
+    premarg = {}
+
+    def __init__(self, lightcurve, model):
+        self.lightcurve = lightcurve
+        self.model = deepcopy(model)
+        self.ranges = deepcopy(model.ranges)
+        self.confidence = 0.999
+        self.noise_ev = self.noise_evidence()
+
+    # bayes.py:623-639
+    def noise_evidence(self):
+        var = estimate_noise_tv(self.lightcurve.clc, 1.0)[0] ** 2
+        clc = self.lightcurve.clc
+        return -0.5 * len(clc) * np.log(2. * pi * var) - np.sum(clc ** 2) / (2. * var)
+
+    def _check(self, bglen, nsinusoids):
+        if bglen is None or nsinusoids != 0:
+            raise NotImplementedError("the whole-series background (bglen=None / nsinusoids != 0, "
+                                      "bayes.py:278-307) is not part of the sliding-window GPU path")
+        if bglen % 2 == 0:
+            print("Error... Background length (bglen) must be an odd number")      # bayes.py:229-233
+            return False
+        return True
+
+    def bayes_factors_marg_poly_bgd(self, bglen=55, bgorder=4, nsinusoids=0, noiseestmethod='powerspectrum',
+                                    psestfrac=0.5, tvsigma=1.0, halfrange=True, ncpus=None):
+        """Log Bayes factor of "model + polynomial background" versus Gaussian noise for every
+        grid point and every sample, amplitudes marginalised analytically (bayes.py:153-437).
+        Sets ``self.lnBmargAmp`` (shape ``model.shape + (N,)``) and ``self.premarg``.
+        ``ncpus`` is accepted for compatibility and ignored."""
+        if not self._check(bglen, nsinusoids):
+            return None
+        sk = estimate_sigma(self.lightcurve, bglen, bgorder, noiseestmethod, psestfrac, tvsigma)
+        if sk is None:
+            return None
+        lc, model = self.lightcurve, self.model
+        N = len(lc.cts)
+        if bglen > N:
+            print("Error... bglen is greater than the data length!")
+            return None
+        mts = window_times(model.ts, bglen, model.t0)
+        noisevar = sk ** 2 + np.asarray(lc.cle, dtype=float) ** 2             # bayes.py:312
+        hyp = hypothesis_from_model(model, mts, halfrange, ranges=self.ranges)
+        ctx = _lib.default_context()
+        plan = _lib.Plan(ctx, bglen, background_models(bglen, bgorder), mts, [hyp])
+        try:
+            lnB, _ = plan.window_lnB(0, lc.clc, lc.cle, sk, _sumlogsigma(noisevar))
+        finally:
+            plan.close()
+        self.lnBmargAmp = lnB.reshape(tuple(model.shape) + (N,))
+        self.premarg = np.copy(self.lnBmargAmp)
+
+    def bayes_factors_marg_poly_bgd_only(self, bglen=55, bgorder=4, nsinusoids=0, noiseestmethod='powerspectrum',
+                                         psestfrac=0.5, tvsigma=1.0):
+        """Log Bayes factor of a polynomial background alone versus Gaussian noise (bayes.py:439-563)."""
+        if not self._check(bglen, nsinusoids):
+            return None
+        lc = self.lightcurve
+        N = len(lc.cts)
+        if bglen > N:
+            print("Error... bglen is greater than the data length!")
+            return None
+        sk = estimate_sigma(lc, bglen, bgorder, noiseestmethod, psestfrac, tvsigma)
+        if sk is None:
+            return None
+        noisevar = sk ** 2 + np.asarray(lc.cle, dtype=float) ** 2
+        ctx = _lib.default_context()
+        plan = _lib.Plan(ctx, bglen, background_models(bglen, bgorder), np.asarray(lc.cts[:bglen], dtype=float), [])
+        try:
+            _, B = plan.window_lnB(0, lc.clc, lc.cle, sk, _sumlogsigma(noisevar), want_lnB=False, want_bg=True)
+        finally:
+            plan.close()
+        self.lnBmargBackground = B
+        return B
+
+    def marginalise(self, pname):
+        """Integrate ``lnBmargAmp`` over one parameter with the log-space trapezium rule, or drop
+        the axis if the parameter is fixed (bayes.py:565-604).  Returns a new :class:`Bayes`."""
+        arr = self.lnBmargAmp
+        places = self.ranges[pname]
+        axis = self.model.paramnames.index(pname)
+        if len(places) > 1:
+            moved = np.moveaxis(arr, axis, 0)
+            x = _lib.logtrapz_axis0(_lib.default_context(), moved, places)
+        else:
+            x = np.reshape(arr, tuple(s for i, s in enumerate(arr.shape) if i != axis))
+        model = copy(self.model)
+        model.paramnames = [p for p in self.model.paramnames if p != pname]
+        model.shape = [s for i, s in enumerate(self.model.shape) if i != axis]
+        B = Bayes(self.lightcurve, model)
+        ranges = copy(self.ranges)
+        del ranges[pname]
+        B.ranges = ranges
+        B.lnBmargAmp = x
+        return B
+
+    def marginalise_full(self):
+        """bayes.py:606-621"""
+        A = self
+        for p in list(self.ranges):
+            A = A.marginalise(p)
+        return A
+
+
+class ParameterEstimationGrid:
+    """Posterior of a model's parameters on a grid for a short light-curve chunk
+    (bayes.py:688-1391); the likelihood of every grid point is evaluated on the GPU."""
+
+    def __init__(self, modelType=None, lightcurve=None):
+        self.modelType = None
+        self.model = None
+        self.paramNames = None
+        self.paramValues = {}
+        self.noiseSigma = None
+        self.prior = None
+        self.posterior = None
+        self.margposteriors = {}
+        self.maxposterior = None
+        self.maxpostparams = {}
+        if lightcurve is None:
+            print("A lightcurve is required as input")
+        else:
+            self.lightcurve = deepcopy(lightcurve)
+        if modelType is None:
+            print("Specify the model type with set_model_type()")
+        elif modelType.lower() in ('flare', 'transit'):
+            self.set_model_type(modelType)
+        else:
+            print("Unknown model type")
+        self.set_sigma(self.lightcurve)
+
+    def set_model_type(self, modelType):
+        """bayes.py:735-769"""
+        from . import models
+        self.modelType = modelType.lower()
+        cls = {'flare': models.Flare, 'transit': models.Transit, 'gaussian': models.Gaussian,
+               'expdecay': models.Expdecay, 'impulse': models.Impulse, 'step': models.Step}[self.modelType]
+        self.model = cls(self.lightcurve.cts)
+        self.paramNames = self.model.paramnames
+        self.prior = self.model.prior
+
+    def set_grid(self, ranges={}):
+        """bayes.py:771-816.  As in the reference, single values are stored as float32."""
+        if len(ranges) == 0:
+            print("Must specify a dictionary of ranges")
+            return
+        if len(self.model.ranges) == 0:
+            self.model.set_params(ranges)
+        for p in self.paramNames:
+            if p not in ranges:
+                print("Error. The parameter %s is not in the dictionary" % p)
+                return
+            irange = ranges[p]
+            if not isinstance(irange, tuple):
+                irange = (irange,)
+            if len(irange) == 3:
+                if irange[0] < irange[1] and irange[2] > 1:
+                    vals = np.linspace(irange[0], irange[1], int(irange[2]))
+                else:
+                    print("%s range has an upper bound smaller than the lower bound! Try again." % p)
+                    return
+            elif len(irange) == 1:
+                vals = np.array([irange[0]], dtype='float32')
+            self.paramValues[p] = vals
+
+    def lightcurve_chunk(self, centidx, length):
+        """bayes.py:818-846"""
+        ll = len(self.lightcurve.cts)
+        dl = int(length / 2)
+        startidx = max(centidx - dl, 0)
+        endidx = centidx + dl + 1
+        if endidx > ll - 1:
+            endidx = ll
+        lc = self.lightcurve
+        lc.cts, lc.clc, lc.cle = lc.cts[startidx:endidx], lc.clc[startidx:endidx], lc.cle[startidx:endidx]
+
+    def lightcurve_dynamic_range(self):
+        return (np.amin(self.lightcurve.clc), np.amax(self.lightcurve.clc))
+
+    def set_sigma(self, lightcurve, detrend=True, dtlen=55, dtorder=4, noiseestmethod='powerspectrum', estfrac=0.5,
+                  tvsigma=1.0):
+        """bayes.py:862-910"""
+        tmpcurve = copy(lightcurve)
+        if detrend:
+            tmpcurve.detrend(method='savitzkygolay', nbins=dtlen, order=dtorder)
+        if noiseestmethod == 'powerspectrum':
+            sigma = estimate_noise_ps(tmpcurve, estfrac=estfrac)[0]
+        elif noiseestmethod == 'tailveto':
+            sigma = estimate_noise_tv(tmpcurve.clc, sigma=tvsigma)[0]
+        elif noiseestmethod == 'std':
+            sigma = np.std(tmpcurve.clc)
+        else:
+            print("Noise estimation method must be 'powerspectrum' or 'tailveto'")
+            sigma = None
+        self.noiseSigma = sigma
+
+    def calculate_posterior(self, paramValues=None, lightcurve=None, sigma=None, margbackground=True, bgorder=4,
+                            ncpus=None):
+        """Unnormalised log posterior on the grid (bayes.py:912-1055).  ``ncpus`` is ignored."""
+        if paramValues is not None:
+            pv = paramValues
+            for p in self.paramNames:
+                if p not in pv:
+                    print("Parameter %s is not in the supplied paramValues" % p)
+                    return None
+            if len(pv) != len(self.paramNames):
+                print("Input parameter values dictionary is not the right length!")
+                return None
+        else:
+            pv = self.paramValues
+        lc = lightcurve if lightcurve is not None else self.lightcurve
+        if getattr(lc, "detrended", False) and getattr(lc, "detrend_method", None) == 'savitzkygolay':
+            raise NotImplementedError("posterior on a Savitzky-Golay detrended chunk (bayes.py:1019-1021) "
+                                      "is not covered by the GPU path")
+        # NOTE (as the reference, bayes.py:1039 and :1046): the likelihood always uses
+        # self.noiseSigma, even when ``sigma`` is passed.
+        sk = self.noiseSigma
+        dl = len(lc.cts)
+        sp = [len(pv[p]) for p in self.paramNames]
+        mesh = np.meshgrid(*[np.asarray(pv[p], dtype=float) for p in self.paramNames], indexing="ij")
+        params = np.zeros((int(np.prod(sp)), 4))
+        for i, m in enumerate(mesh):
+            params[:, i] = m.ravel()
+        pdicts = ({p: pv[p][q[i]] for i, p in enumerate(self.paramNames)} for q in np.ndindex(*sp))
+        logprior = np.array([self.prior(pd) for pd in pdicts], dtype=float)
+        polyms = None
+        if margbackground:
+            ts01 = np.linspace(0, 1, dl)
+            polyms = np.array([ts01 ** i for i in range(bgorder + 1)])
+        post = _lib.pe_grid(_lib.default_context(), self.model.device_kind, self.model.reverse, lc.cts, lc.clc,
+                            params, logprior, bgorder + 1, polyms, sk, margbackground)
+        self.posterior = post.reshape(tuple(sp))
+
+    # ---- post-processing (host; bayes.py:1057-1301) ---------------------------------------
+    def marginalised_posterior(self, parameter=None):
+        if parameter not in self.paramNames:
+            print("Given parameter (%s) is not in model" % parameter)
+            return None
+        if self.posterior is None:
+            print("Posterior not yet defined!")
+            return None
+        idx = 0
+        shortpars = []
+        for i, p in enumerate(self.paramNames):
+            if parameter.lower() == p:
+                idx = i
+            else:
+                shortpars.append(p)
+        nump = len(self.paramNames)
+        pv = self.paramValues
+        margp = np.copy(self.posterior)
+        if idx < nump - 1:
+            margp = np.rollaxis(margp, idx, nump)
+        for p in shortpars:
+            if margp.shape[0] == 1:
+                margp = margp[0]
+            else:
+                margp = np.apply_along_axis(logtrapz, 0, margp, np.asarray(pv[p], dtype=float))
+        if len(margp) > 1:
+            area = logtrapz(margp, np.asarray(pv[parameter.lower()], dtype=float))
+        else:
+            area = 1.
+        margp = np.exp(margp - area)
+        self.margposteriors[parameter.lower()] = np.copy(margp)
+        return margp
+
+    def marginalise_all(self):
+        for p in self.paramNames:
+            self.marginalised_posterior(p)
+
+    def marginalised_posterior_2D(self, parameters=None):
+        if not isinstance(parameters, list) or len(parameters) != 2:
+            print("Must supply a list of two parameters")
+            return None
+        for p in parameters:
+            if p.lower() not in self.paramNames:
+                print("Given parameter (%s) is not in model" % p)
+                return None
+        if self.posterior is None:
+            print("Posterior not yet defined!")
+            return None
+        nump = len(self.paramNames)
+        pv = self.paramValues
+        if nump < 3:
+            print("No need to marginalise, posterior is already 2d or 1d")
+            return None
+        idx1 = idx2 = 0
+        shortpars = []
+        for i, p in enumerate(self.paramNames):
+            if parameters[0].lower() == p:
+                idx1 = i
+            elif parameters[1].lower() == p:
+                idx2 = i
+            else:
+                shortpars.append(p)
+        margp = np.copy(self.posterior)
+        if idx2 < nump - 1:
+            margp = np.rollaxis(margp, idx2, nump)
+            if idx2 < idx1:
+                idx1 = idx1 - 1
+        if idx1 < nump - 2:
+            margp = np.rollaxis(margp, idx1, nump - 1)
+        for p in shortpars:
+            if margp.shape[0] == 1:
+                margp = margp[0]
+            else:
+                margp = np.apply_along_axis(logtrapz, 0, margp, np.asarray(pv[p], dtype=float))
+        area = np.apply_along_axis(logtrapz, 0, np.copy(margp), np.asarray(pv[parameters[0].lower()], dtype=float))
+        area = logtrapz(area, np.asarray(pv[parameters[1].lower()], dtype=float))
+        return np.exp(margp - area)
+
+    def maximum_posterior(self):
+        if self.posterior is None:
+            print("Posterior not defined")
+            return None
+        q = np.unravel_index(self.posterior.argmax(), self.posterior.shape)
+        self.maxposterior = self.posterior[q]
+        for j, p in enumerate(self.paramNames):
+            self.maxpostparams[p] = self.paramValues[p][q[j]]
+        return self.maxposterior, self.maxpostparams
+
+    def maximum_posterior_snr(self):
+        if self.maxposterior is None:
+            self.maximum_posterior()
+        m = self.model.model(self.maxpostparams, ts=self.lightcurve.cts)
+        return np.sqrt(np.sum(m ** 2)) / self.noiseSigma
+
+    def maximum_posterior_ew(self):
+        if self.maxposterior is None:
+            self.maximum_posterior()
+        m = self.model.model(self.maxpostparams, ts=self.lightcurve.cts)
+        return getattr(np, 'trapezoid', getattr(np, 'trapz', None))(m, self.lightcurve.cts) / np.median(self.lightcurve.clc - m + self.lightcurve.dc)

@@ -1,0 +1,616 @@
+// bfl_abi.cu -- the C ABI of libbfl.so (see include/bfl.h): context / plan management,
+// host<->device staging and kernel orchestration.  No CPU fallback: without a CUDA device
+// every compute entry point fails with BFL_ERR_NODEVICE.
+#include "../../include/bfl.h"
+#include "bfl_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace bfl;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      char buf__[512];                                                                             \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),      \
+               __FILE__, __LINE__);                                                                \
+      return fail(e__ == cudaErrorMemoryAllocation ? BFL_ERR_OOM : BFL_ERR_CUDA, buf__);           \
+    }                                                                                              \
+  } while (0)
+
+struct bfl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  LaunchStats stats;
+  std::map<std::string, std::pair<void*, size_t>> pool;   // grow-only named device buffers
+
+  int get(const char* name, size_t bytes, void** out) {
+    auto& e = pool[name];
+    if (e.second < bytes) {
+      if (e.first) {
+        cudaStreamSynchronize(stream);
+        cudaFree(e.first);
+        e.first = nullptr;
+        e.second = 0;
+      }
+      size_t want = bytes + bytes / 4 + 256;
+      cudaError_t err = cudaMalloc(&e.first, want);
+      if (err != cudaSuccess) {
+        e.first = nullptr;
+        return fail(BFL_ERR_OOM, std::string("cudaMalloc failed for ") + name + ": " + cudaGetErrorString(err));
+      }
+      e.second = want;
+    }
+    *out = e.first;
+    return BFL_OK;
+  }
+};
+
+struct bfl_plan {
+  bfl_ctx* ctx = nullptr;
+  PlanView pv{};
+  std::vector<int> ngrid;                 // per hypothesis, uncompacted
+  std::vector<void*> allocs;
+  std::vector<int> h_gorig;
+};
+
+extern "C" {
+
+int bfl_version(void) { return BFL_VERSION; }
+const char* bfl_last_error(void) { return g_err.c_str(); }
+
+int bfl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int bfl_ctx_create(int device, void* stream, bfl_ctx** out) {
+  if (!out) return fail(BFL_ERR_ARG, "ctx output pointer is null");
+  *out = nullptr;
+  if (bfl_device_count() <= 0)
+    return fail(BFL_ERR_NODEVICE, "no CUDA device available: libbfl has no CPU fallback");
+  if (device < 0) CK(cudaGetDevice(&device));
+  CK(cudaSetDevice(device));
+  bfl_ctx* c = new (std::nothrow) bfl_ctx();
+  if (!c) return fail(BFL_ERR_OOM, "out of host memory");
+  c->device = device;
+  CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(BFL_ERR_CUDA, cudaGetErrorString(e)); }
+    c->own_stream = true;
+  }
+  *out = c;
+  return BFL_OK;
+}
+
+int bfl_ctx_destroy(bfl_ctx* c) {
+  if (!c) return BFL_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->pool)
+    if (kv.second.first) cudaFree(kv.second.first);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return BFL_OK;
+}
+
+int bfl_ctx_sync(bfl_ctx* c) {
+  if (!c) return fail(BFL_ERR_ARG, "null context");
+  CK(cudaStreamSynchronize(c->stream));
+  return BFL_OK;
+}
+
+int64_t bfl_ctx_launch_count(const bfl_ctx* c) { return c ? c->stats.launches : 0; }
+
+// --------------------------------------------------------------------------------------
+static int plan_alloc(bfl_plan* p, size_t bytes, void** out) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 8);
+  if (e != cudaSuccess) return fail(BFL_ERR_OOM, std::string("cudaMalloc(plan): ") + cudaGetErrorString(e));
+  p->allocs.push_back(d);
+  *out = d;
+  return BFL_OK;
+}
+
+int bfl_plan_destroy(bfl_plan* p) {
+  if (!p) return BFL_OK;
+  if (p->ctx) {
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+  }
+  for (void* d : p->allocs) cudaFree(d);
+  delete p;
+  return BFL_OK;
+}
+
+int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const double* mts,
+                    const bfl_hypothesis* hyps, int nhyp, bfl_plan** out) {
+  if (!c || !out || !bgmodels || !mts) return fail(BFL_ERR_ARG, "null argument to bfl_plan_create");
+  *out = nullptr;
+  if (W < 3 || W % 2 == 0)   // bayes.py:229-233
+    return fail(BFL_ERR_ARG, "Error... Background length (bglen) must be an odd number");
+  if (W > MAXW) return fail(BFL_ERR_UNSUPPORTED, "bglen > 255 is not supported");
+  if (P < 1 || P > MAXP) return fail(BFL_ERR_UNSUPPORTED, "bgorder must be in 0..5");
+  if (nhyp < 0 || nhyp > MAXH) return fail(BFL_ERR_UNSUPPORTED, "too many hypotheses in one plan (max 8)");
+  if (nhyp > 0 && !hyps) return fail(BFL_ERR_ARG, "null hypothesis array");
+  CK(cudaSetDevice(c->device));
+
+  bfl_plan* p = new (std::nothrow) bfl_plan();
+  if (!p) return fail(BFL_ERR_OOM, "out of host memory");
+  p->ctx = c;
+  const int WP = W + 1;
+  PlanView& pv = p->pv;
+  pv.W = W; pv.WP = WP; pv.P = P; pv.nhyp = nhyp;
+
+  std::vector<TemplDesc> desc;
+  std::vector<double> lp, lw, table_rows;
+  std::vector<int> gorig, table_at;
+  pv.hyp_begin[0] = 0;
+  for (int h = 0; h < nhyp; h++) {
+    const bfl_hypothesis& hy = hyps[h];
+    if (hy.ngrid < 0 || !hy.logprior || !hy.logweight || (hy.kind != BFL_MODEL_TABLE && !hy.params) ||
+        (hy.kind == BFL_MODEL_TABLE && !hy.table) || hy.kind < 0 || hy.kind > BFL_MODEL_TABLE) {
+      delete p;
+      return fail(BFL_ERR_ARG, "malformed hypothesis descriptor");
+    }
+    p->ngrid.push_back(hy.ngrid);
+    pv.hyp_half[h] = hy.halfrange ? 1 : 0;
+    for (int g = 0; g < hy.ngrid; g++) {
+      const double pr = hy.logprior[g];
+      if (!(pr > -INFINITY) || std::isnan(pr)) continue;   // masked grid point: row stays -inf (bayes.py:358-363)
+      TemplDesc d{};
+      d.kind = hy.kind; d.reverse = hy.reverse;
+      for (int i = 0; i < 4; i++) d.p[i] = hy.params ? hy.params[(size_t)g * 4 + i] : 0.0;
+      if (hy.kind == BFL_MODEL_TABLE) {
+        table_at.push_back((int)desc.size());
+        table_rows.insert(table_rows.end(), hy.table + (size_t)g * W, hy.table + (size_t)(g + 1) * W);
+      }
+      desc.push_back(d);
+      lp.push_back(pr);
+      lw.push_back(hy.logweight[g]);
+      gorig.push_back(g);
+    }
+    pv.hyp_begin[h + 1] = (int)desc.size();
+  }
+  const int G = (int)desc.size();
+  pv.G = G;
+  p->h_gorig = gorig;
+
+  // background basis, its pair products, and an orthonormalised copy (modified Gram-Schmidt
+  // with re-orthogonalisation in extended precision; log det G = 2 sum log r_jj)
+  std::vector<double> bg((size_t)P * WP, 0.0), bb((size_t)(P * (P + 1) / 2) * WP, 0.0), qb((size_t)P * WP, 0.0);
+  for (int j = 0; j < P; j++)
+    for (int w = 0; w < W; w++) bg[(size_t)j * WP + w] = bgmodels[(size_t)j * W + w];
+  {
+    int pq = 0;
+    for (int a = 0; a < P; a++)
+      for (int b = a; b < P; b++, pq++)
+        for (int w = 0; w < W; w++) bb[(size_t)pq * WP + w] = bgmodels[(size_t)a * W + w] * bgmodels[(size_t)b * W + w];
+  }
+  long double logdet = 0.0L;
+  {
+    std::vector<std::vector<long double>> q(P, std::vector<long double>(W));
+    for (int j = 0; j < P; j++) {
+      std::vector<long double> v(W);
+      for (int w = 0; w < W; w++) v[w] = (long double)bgmodels[(size_t)j * W + w];
+      for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < j; i++) {
+          long double r = 0.0L;
+          for (int w = 0; w < W; w++) r += q[i][w] * v[w];
+          for (int w = 0; w < W; w++) v[w] -= r * q[i][w];
+        }
+      long double nrm = 0.0L;
+      for (int w = 0; w < W; w++) nrm += v[w] * v[w];
+      nrm = sqrtl(nrm);
+      if (!(nrm > 0.0L)) { delete p; return fail(BFL_ERR_ARG, "background basis is rank deficient"); }
+      for (int w = 0; w < W; w++) q[j][w] = v[w] / nrm;
+      logdet += 2.0L * logl(nrm);
+      for (int w = 0; w < W; w++) qb[(size_t)j * WP + w] = (double)q[j][w];
+    }
+  }
+  pv.logdetG = (double)logdet;
+
+  void *d_desc, *d_mts, *d_raw, *d_hat, *d_Kg, *d_lp, *d_lw, *d_gorig, *d_bg, *d_bb, *d_qb;
+  int rc;
+#define PA(ptr, bytes) if ((rc = plan_alloc(p, (bytes), &(ptr))) != BFL_OK) { bfl_plan_destroy(p); return rc; }
+  PA(d_desc, sizeof(TemplDesc) * (size_t)std::max(G, 1));
+  PA(d_mts, sizeof(double) * (size_t)W);
+  PA(d_raw, sizeof(double) * (size_t)std::max(G, 1) * WP);
+  PA(d_hat, sizeof(double) * (size_t)std::max(G, 1) * WP);
+  PA(d_Kg, sizeof(double) * (size_t)std::max(G, 1));
+  PA(d_lp, sizeof(double) * (size_t)std::max(G, 1));
+  PA(d_lw, sizeof(double) * (size_t)std::max(G, 1));
+  PA(d_gorig, sizeof(int) * (size_t)std::max(G, 1));
+  PA(d_bg, sizeof(double) * bg.size());
+  PA(d_bb, sizeof(double) * bb.size());
+  PA(d_qb, sizeof(double) * qb.size());
+#undef PA
+  cudaStream_t s = c->stream;
+#define CKP(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { bfl_plan_destroy(p); \
+    return fail(BFL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } } while (0)
+  if (G > 0) {
+    CKP(cudaMemcpyAsync(d_desc, desc.data(), sizeof(TemplDesc) * (size_t)G, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_lp, lp.data(), sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_lw, lw.data(), sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_gorig, gorig.data(), sizeof(int) * (size_t)G, cudaMemcpyHostToDevice, s));
+  }
+  CKP(cudaMemcpyAsync(d_mts, mts, sizeof(double) * (size_t)W, cudaMemcpyHostToDevice, s));
+  CKP(cudaMemcpyAsync(d_bg, bg.data(), sizeof(double) * bg.size(), cudaMemcpyHostToDevice, s));
+  CKP(cudaMemcpyAsync(d_bb, bb.data(), sizeof(double) * bb.size(), cudaMemcpyHostToDevice, s));
+  CKP(cudaMemcpyAsync(d_qb, qb.data(), sizeof(double) * qb.size(), cudaMemcpyHostToDevice, s));
+  CKP(cudaMemsetAsync(d_raw, 0, sizeof(double) * (size_t)std::max(G, 1) * WP, s));
+  CKP(launch_gen_templates((const TemplDesc*)d_desc, G, (const double*)d_mts, W, WP, (double*)d_raw, s, &c->stats));
+  for (size_t i = 0; i < table_at.size(); i++)
+    CKP(cudaMemcpyAsync((double*)d_raw + (size_t)table_at[i] * WP, table_rows.data() + i * W, sizeof(double) * (size_t)W,
+                        cudaMemcpyHostToDevice, s));
+  CKP(launch_plan_orthonormalise((const double*)d_raw, (const double*)d_qb, G, W, WP, P, (double*)d_hat,
+                                 (double*)d_Kg, s, &c->stats));
+  CKP(cudaStreamSynchronize(s));   // host vectors above go out of scope
+#undef CKP
+  pv.raw = (const double*)d_raw; pv.hat = (const double*)d_hat; pv.Kg = (const double*)d_Kg;
+  pv.lp = (const double*)d_lp; pv.lw = (const double*)d_lw; pv.gorig = (const int*)d_gorig;
+  pv.bg = (const double*)d_bg; pv.bb = (const double*)d_bb; pv.qb = (const double*)d_qb;
+  *out = p;
+  return BFL_OK;
+}
+
+int bfl_plan_templates(bfl_plan* p, int ihyp, double* out) {
+  if (!p || !out || ihyp < 0 || ihyp >= p->pv.nhyp) return fail(BFL_ERR_ARG, "bad argument to bfl_plan_templates");
+  const PlanView& pv = p->pv;
+  CK(cudaSetDevice(p->ctx->device));
+  const int g0 = pv.hyp_begin[ihyp], g1 = pv.hyp_begin[ihyp + 1];
+  std::vector<double> tmp((size_t)std::max(g1 - g0, 1) * pv.WP);
+  std::memset(out, 0, sizeof(double) * (size_t)p->ngrid[ihyp] * pv.W);
+  if (g1 > g0) {
+    CK(cudaMemcpyAsync(tmp.data(), pv.raw + (size_t)g0 * pv.WP, sizeof(double) * (size_t)(g1 - g0) * pv.WP,
+                       cudaMemcpyDeviceToHost, p->ctx->stream));
+    CK(cudaStreamSynchronize(p->ctx->stream));
+    for (int g = g0; g < g1; g++)
+      std::memcpy(out + (size_t)p->h_gorig[g] * pv.W, tmp.data() + (size_t)(g - g0) * pv.WP, sizeof(double) * (size_t)pv.W);
+  }
+  return BFL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, bool need_general, bool need_bg,
+                         bool need_part, Scratch& sc) {
+  const int64_t nk = sv.k1 - sv.k0;
+  int KT = 1;
+  sc.gchunk = pick_gchunk(std::max(pv.G, 1), pv.W, (int64_t)sv.B * nk, c->sm_count, &KT);
+  sc.KT = KT;
+  sc.NC = (std::max(pv.G, 1) + sc.gchunk - 1) / sc.gchunk;
+  int rc;
+  void* ptr;
+  if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;
+  if ((rc = c->get("halflogv", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.halflogv = (double*)ptr;
+  if ((rc = c->get("uconst", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.uconst = (double*)ptr;
+  sc.dw = sc.uu = nullptr;
+  if (need_general) {
+    if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
+    if ((rc = c->get("uu", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.uu = (double*)ptr;
+  }
+  sc.part = nullptr;
+  if (need_part) {
+    if ((rc = c->get("part", sizeof(double2) * (size_t)std::max(pv.nhyp, 1) * sc.NC * sv.B * nk, &ptr))) return rc;
+    sc.part = (double2*)ptr;
+  }
+  sc.bgabs = nullptr;
+  if (need_bg) {
+    if ((rc = c->get("bgabs", sizeof(double) * (size_t)sv.B * nk, &ptr))) return rc; sc.bgabs = (double*)ptr;
+  }
+  return BFL_OK;
+}
+
+static bool range_has_edges(const PlanView& pv, const SeriesView& sv) {
+  const int H = pv.W / 2;
+  return sv.k0 < H || sv.k1 > sv.N - H;
+}
+
+static int check_series(const PlanView& pv, const SeriesView& sv) {
+  const int H = pv.W / 2;
+  if (sv.B < 1 || sv.N < pv.W) return fail(BFL_ERR_ARG, "Error... bglen is greater than the data length!");
+  if (sv.k0 < 0 || sv.k1 > sv.N || sv.k0 >= sv.k1) return fail(BFL_ERR_ARG, "bad sample range");
+  const int64_t need_lo = std::max<int64_t>(0, sv.k0 - H), need_hi = std::min<int64_t>(sv.N, sv.k1 + H);
+  if (sv.seg0 > need_lo || sv.seg0 + sv.seglen < need_hi)
+    return fail(BFL_ERR_ARG, "segment does not cover the requested samples plus their halo");
+  return BFL_OK;
+}
+
+static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView& sv, double* d_lnO, double* d_marg) {
+  const PlanView& pv = p->pv;
+  if (pv.nhyp < 1) return fail(BFL_ERR_ARG, "the detector needs a signal hypothesis (plan hypothesis 0)");
+  int rc = check_series(pv, sv);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  const bool edges = range_has_edges(pv, sv);
+  const bool need_general = !sv.const_var || edges;
+  const int nnoise = pv.nhyp - 1 + (noisepoly ? 1 : 0);
+  const bool need_bg = (d_marg != nullptr) || nnoise == 0;
+  Scratch sc{};
+  if ((rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc))) return rc;
+  cudaStream_t s = c->stream;
+  CK(launch_prep(sv, sc, need_general, s, &c->stats));
+  if (sv.const_var) {
+    CK(launch_window_fast_lse(pv, sv, sc, s, &c->stats));
+    if (need_bg) CK(launch_bgproj(pv, sv, sc, s, &c->stats));
+    if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));
+  } else {
+    CK(launch_window_general_lse(pv, sv, sc, false, s, &c->stats));
+  }
+  CK(launch_combine(pv, sv, sc, noisepoly, d_lnO, d_marg, s, &c->stats));
+  return BFL_OK;
+}
+
+int bfl_detector_odds_dev(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* d_clc, const double* d_cle,
+                          int const_var, const double* d_sk, int32_t B, int64_t N, int64_t seg0, int64_t seglen,
+                          int64_t k0, int64_t k1, double* d_lnO) {
+  if (!c || !p || !d_clc || !d_sk || !d_lnO) return fail(BFL_ERR_ARG, "null argument to bfl_detector_odds_dev");
+  SeriesView sv{d_clc, d_cle, d_sk, B, N, seg0, seglen, k0, k1, (d_cle == nullptr || const_var) ? 1 : 0};
+  return detector_run(c, p, noisepoly, sv, d_lnO, nullptr);
+}
+
+static bool rows_constant(const double* a, int B, int64_t N) {
+  for (int b = 0; b < B; b++) {
+    const double* r = a + (size_t)b * N;
+    const double v = r[0] * r[0];
+    for (int64_t i = 1; i < N; i++)
+      if (r[i] * r[i] != v) return false;
+  }
+  return true;
+}
+
+int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc, const double* cle,
+                      const double* sk, int32_t B, int64_t N, double* out_lnO, double* out_marg) {
+  if (!c || !p || !clc || !sk || !out_lnO) return fail(BFL_ERR_ARG, "null argument to bfl_detector_odds");
+  if (B < 1 || N < 1) return fail(BFL_ERR_ARG, "empty batch");
+  CK(cudaSetDevice(c->device));
+  const bool cv = (cle == nullptr) || rows_constant(cle, B, N);
+  const size_t nb = sizeof(double) * (size_t)B * N;
+  void *d_clc, *d_cle = nullptr, *d_sk, *d_lnO, *d_marg = nullptr;
+  int rc;
+  if ((rc = c->get("in_clc", nb, &d_clc))) return rc;
+  if (cle && (rc = c->get("in_cle", nb, &d_cle))) return rc;
+  if ((rc = c->get("in_sk", sizeof(double) * (size_t)B, &d_sk))) return rc;
+  if ((rc = c->get("out_lnO", nb, &d_lnO))) return rc;
+  if (out_marg && (rc = c->get("out_marg", nb * (size_t)(p->pv.nhyp + 1), &d_marg))) return rc;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(d_clc, clc, nb, cudaMemcpyHostToDevice, s));
+  if (cle) CK(cudaMemcpyAsync(d_cle, cle, nb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+  SeriesView sv{(const double*)d_clc, (const double*)d_cle, (const double*)d_sk, B, N, 0, N, 0, N, cv ? 1 : 0};
+  if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO, (double*)d_marg))) return rc;
+  CK(cudaMemcpyAsync(out_lnO, d_lnO, nb, cudaMemcpyDeviceToHost, s));
+  if (out_marg) CK(cudaMemcpyAsync(out_marg, d_marg, nb * (size_t)(p->pv.nhyp + 1), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BFL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+__global__ void k_fill(double* p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int bfl_window_lnB(bfl_ctx* c, bfl_plan* p, int ihyp, const double* clc, const double* cle, double sk, int64_t N,
+                   double sumlogsigma, double* out_lnB, double* out_bg) {
+  if (!c || !p || !clc) return fail(BFL_ERR_ARG, "null argument to bfl_window_lnB");
+  const PlanView& pv = p->pv;
+  if (out_lnB && (ihyp < 0 || ihyp >= pv.nhyp)) return fail(BFL_ERR_ARG, "hypothesis index out of range");
+  if (!out_lnB) ihyp = -1;
+  CK(cudaSetDevice(c->device));
+  const bool cv = (cle == nullptr) || rows_constant(cle, 1, N);
+  const size_t nb = sizeof(double) * (size_t)N;
+  void *d_clc, *d_cle = nullptr, *d_sk, *d_out = nullptr;
+  int rc;
+  if ((rc = c->get("in_clc", nb, &d_clc))) return rc;
+  if (cle && (rc = c->get("in_cle", nb, &d_cle))) return rc;
+  if ((rc = c->get("in_sk", sizeof(double), &d_sk))) return rc;
+  const int ng = (ihyp >= 0) ? p->ngrid[ihyp] : 0;
+  if (ng > 0 && (rc = c->get("out_full", nb * (size_t)ng, &d_out))) return rc;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(d_clc, clc, nb, cudaMemcpyHostToDevice, s));
+  if (cle) CK(cudaMemcpyAsync(d_cle, cle, nb, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_sk, &sk, sizeof(double), cudaMemcpyHostToDevice, s));
+  SeriesView sv{(const double*)d_clc, (const double*)d_cle, (const double*)d_sk, 1, N, 0, N, 0, N, cv ? 1 : 0};
+  if ((rc = check_series(pv, sv))) return rc;
+  Scratch sc{};
+  if ((rc = setup_scratch(c, pv, sv, true, true, false, sc))) return rc;
+  if (ng > 0) {
+    const size_t n = (size_t)ng * N;
+    k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((double*)d_out, n, -INFINITY);
+    c->stats.launches++;
+  }
+  CK(launch_prep(sv, sc, true, s, &c->stats));
+  if (cv) {
+    CK(launch_bgproj(pv, sv, sc, s, &c->stats));
+    if (ihyp >= 0) CK(launch_window_fast_full(pv, ihyp, sv, sc, sumlogsigma, (double*)d_out, s, &c->stats));
+    CK(launch_window_general_full(pv, ihyp, sv, sc, true, sumlogsigma, (double*)d_out, s, &c->stats));
+  } else {
+    CK(launch_window_general_full(pv, ihyp, sv, sc, false, sumlogsigma, (double*)d_out, s, &c->stats));
+  }
+  if (out_lnB && ng > 0) CK(cudaMemcpyAsync(out_lnB, d_out, nb * (size_t)ng, cudaMemcpyDeviceToHost, s));
+  if (out_bg) CK(cudaMemcpyAsync(out_bg, sc.bgabs, nb, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (out_bg)
+    for (int64_t i = 0; i < N; i++) out_bg[i] += sumlogsigma;   // general.pyx:363
+  return BFL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+int bfl_threshold(bfl_ctx* c, const double* lnO, int64_t n, double thresh, int32_t expand, int64_t* segs,
+                  double* maxval, int64_t* maxidx, int32_t max_segs, int32_t* nsegs) {
+  if (!c || !lnO || !nsegs) return fail(BFL_ERR_ARG, "null argument to bfl_threshold");
+  *nsegs = 0;
+  if (n <= 0) return BFL_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int cap = (int)std::min<int64_t>(n / 2 + 2, 1 << 24);
+  void *d_l, *d_st, *d_sp, *d_cnt;
+  int rc;
+  if ((rc = c->get("thr_lnO", sizeof(double) * (size_t)n, &d_l))) return rc;
+  if ((rc = c->get("thr_st", sizeof(int64_t) * (size_t)cap, &d_st))) return rc;
+  if ((rc = c->get("thr_sp", sizeof(int64_t) * (size_t)cap, &d_sp))) return rc;
+  if ((rc = c->get("thr_cnt", sizeof(int) * 2, &d_cnt))) return rc;
+  CK(cudaMemcpyAsync(d_l, lnO, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * 2, s));
+  CK(launch_threshold_edges((const double*)d_l, n, thresh, (int64_t*)d_st, (int64_t*)d_sp, (int*)d_cnt, cap, s, &c->stats));
+  int cnt[2] = {0, 0};
+  CK(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (cnt[0] != cnt[1] || cnt[0] > cap) return fail(BFL_ERR_CUDA, "threshold edge extraction overflowed");
+  const int nr = cnt[0];
+  std::vector<int64_t> st(nr), sp(nr);
+  if (nr) {
+    CK(cudaMemcpyAsync(st.data(), d_st, sizeof(int64_t) * (size_t)nr, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(sp.data(), d_sp, sizeof(int64_t) * (size_t)nr, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  std::sort(st.begin(), st.end());
+  std::sort(sp.begin(), sp.end());
+  // expansion and merging of adjacent/overlapping regions: find.py:957-1006
+  std::vector<std::pair<int64_t, int64_t>> fl(nr);
+  for (int i = 0; i < nr; i++) fl[i] = {st[i], sp[i]};
+  if (expand > 0 && nr > 0) {
+    for (auto& sg : fl) {
+      sg.first -= expand; sg.second += expand;
+      if (sg.first < 0) sg.first = 0;
+      if (sg.second >= n) sg.second = n;
+    }
+    if (nr > 1) {
+      std::vector<std::pair<int64_t, int64_t>> merged;
+      size_t j = 0;
+      while (true) {
+        auto cur = fl[j];
+        j++;
+        for (size_t k = j; k < fl.size(); k++) {
+          if (cur.second >= fl[k].first) { cur.second = fl[k].second; j++; } else break;
+        }
+        merged.push_back(cur);
+        if (j >= fl.size()) break;
+      }
+      fl.swap(merged);
+    }
+  }
+  const int nf = (int)fl.size();
+  *nsegs = nf;
+  const int nout = std::min<int>(nf, max_segs);
+  if (nout > 0 && segs) {
+    for (int i = 0; i < nout; i++) { segs[2 * i] = fl[i].first; segs[2 * i + 1] = fl[i].second; }
+  }
+  if (nout > 0 && maxval && maxidx && segs) {
+    void *d_sg, *d_mv, *d_mi;
+    if ((rc = c->get("thr_sg", sizeof(int64_t) * 2 * (size_t)nout, &d_sg))) return rc;
+    if ((rc = c->get("thr_mv", sizeof(double) * (size_t)nout, &d_mv))) return rc;
+    if ((rc = c->get("thr_mi", sizeof(int64_t) * (size_t)nout, &d_mi))) return rc;
+    CK(cudaMemcpyAsync(d_sg, segs, sizeof(int64_t) * 2 * (size_t)nout, cudaMemcpyHostToDevice, s));
+    CK(launch_region_max((const double*)d_l, (const int64_t*)d_sg, nout, (double*)d_mv, (int64_t*)d_mi, s, &c->stats));
+    CK(cudaMemcpyAsync(maxval, d_mv, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(maxidx, d_mi, sizeof(int64_t) * (size_t)nout, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return BFL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+int bfl_pe_grid(bfl_ctx* c, int32_t kind, int32_t reverse, const double* cts, const double* clc, int64_t L,
+                const double* params, const double* logprior, int64_t G, int32_t P, const double* polyms,
+                double sigma, int32_t margbackground, double* out_post) {
+  if (!c || !cts || !clc || !params || !logprior || !out_post) return fail(BFL_ERR_ARG, "null argument to bfl_pe_grid");
+  if (margbackground && !polyms) return fail(BFL_ERR_ARG, "polyms required when margbackground is set");
+  if (kind < 0 || kind >= BFL_MODEL_TABLE) return fail(BFL_ERR_ARG, "bad model kind");
+  if (L < 2 || L > 200) return fail(BFL_ERR_UNSUPPORTED, "chunk length must be in 2..200 samples");
+  if (margbackground && (P < 1 || P > MAXP)) return fail(BFL_ERR_UNSUPPORTED, "bgorder must be in 0..5");
+  if (!margbackground) P = 1;
+  if (G < 1) return BFL_OK;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  void *d_cts, *d_clc, *d_par, *d_lp, *d_poly = nullptr, *d_post;
+  int rc;
+  if ((rc = c->get("pe_cts", sizeof(double) * (size_t)L, &d_cts))) return rc;
+  if ((rc = c->get("pe_clc", sizeof(double) * (size_t)L, &d_clc))) return rc;
+  if ((rc = c->get("pe_par", sizeof(double) * 4 * (size_t)G, &d_par))) return rc;
+  if ((rc = c->get("pe_lp", sizeof(double) * (size_t)G, &d_lp))) return rc;
+  if ((rc = c->get("pe_post", sizeof(double) * (size_t)G, &d_post))) return rc;
+  if ((rc = c->get("pe_poly", sizeof(double) * (size_t)P * L, &d_poly))) return rc;
+  CK(cudaMemcpyAsync(d_cts, cts, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_clc, clc, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_par, params, sizeof(double) * 4 * (size_t)G, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_lp, logprior, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, s));
+  if (margbackground) CK(cudaMemcpyAsync(d_poly, polyms, sizeof(double) * (size_t)P * L, cudaMemcpyHostToDevice, s));
+  CK(launch_pe_grid(kind, reverse, (const double*)d_cts, (const double*)d_clc, (int)L, (const double*)d_par,
+                    (const double*)d_lp, G, P, (const double*)d_poly, sigma, margbackground, (double*)d_post, s,
+                    &c->stats));
+  CK(cudaMemcpyAsync(out_post, d_post, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BFL_OK;
+}
+
+int bfl_logtrapz(bfl_ctx* c, const double* lx, const double* t, int64_t n, int64_t m, double* out) {
+  if (!c || !lx || !t || !out || n < 1 || m < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_logtrapz");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  void *d_lx, *d_t, *d_o;
+  int rc;
+  if ((rc = c->get("lt_lx", sizeof(double) * (size_t)n * m, &d_lx))) return rc;
+  if ((rc = c->get("lt_t", sizeof(double) * (size_t)n, &d_t))) return rc;
+  if ((rc = c->get("lt_o", sizeof(double) * (size_t)m, &d_o))) return rc;
+  CK(cudaMemcpyAsync(d_lx, lx, sizeof(double) * (size_t)n * m, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_t, t, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+  CK(launch_logtrapz((const double*)d_lx, (const double*)d_t, n, m, (double*)d_o, s, &c->stats));
+  CK(cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BFL_OK;
+}
+
+int bfl_fp64_peak_probe(bfl_ctx* c, int32_t iters, double* tflops, double* ms) {
+  if (!c || !tflops) return fail(BFL_ERR_ARG, "null argument to bfl_fp64_peak_probe");
+  if (iters < 1) iters = 2048;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  void* d_sink;
+  int rc;
+  if ((rc = c->get("probe", 64, &d_sink))) return rc;
+  const int blocks = c->sm_count * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(launch_fp64_probe((double*)d_sink, iters / 4 + 1, blocks, s, &c->stats));   // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    CK(cudaEventRecord(e0, s));
+    CK(launch_fp64_probe((double*)d_sink, iters, blocks, s, &c->stats));
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    best = std::min(best, t);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return BFL_OK;
+}
+
+}  // extern "C"

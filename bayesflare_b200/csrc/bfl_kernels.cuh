@@ -1,0 +1,105 @@
+// bfl_kernels.cuh -- kernel launch interface shared by bfl_kernels.cu and bfl_abi.cu.
+// sm_100a only; FP64 vector pipe (no tensor cores: a batched tiny-system solve + correlation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bfl {
+
+constexpr int MAXP = 6;      // polynomial terms (bgorder + 1) the general path is instantiated for
+constexpr int MAXH = 8;      // hypotheses per plan
+constexpr int MAXW = 255;    // window length limit
+
+// one valid (unmasked) grid point of one hypothesis
+struct TemplDesc {
+  int32_t kind;
+  int32_t reverse;
+  double p[4];
+};
+
+// Device-side view of a plan.  All arrays are over the COMPACTED list of valid templates
+// (grid points whose prior is finite), hypotheses stored back to back.
+struct PlanView {
+  int W, WP, P, G, nhyp;
+  int hyp_begin[MAXH + 1];   // ranges in the compacted list
+  int hyp_half[MAXH];        // lastHalfRange flag
+  const double* raw;         // [G][WP] templates as the models define them
+  const double* hat;         // [G][WP] templates orthogonalised against the background basis, unit norm
+  const double* Kg;          // [G] -0.5*log(|m_perp|^2)
+  const double* lp;          // [G] log prior (+ log amplitude prior)
+  const double* lw;          // [G] log trapezium weight
+  const int* gorig;          // [G] ravelled grid index inside its hypothesis
+  const double* bg;          // [P][WP] background basis (monomials on [0,1])
+  const double* bb;          // [P*(P+1)/2][WP] products b_p*b_q (upper triangle, row-major)
+  const double* qb;          // [P][WP] orthonormalised background basis
+  double logdetG;            // log det of the unit-variance background Gram matrix
+};
+
+struct SeriesView {
+  const double* clc;    // dev [B][seglen]
+  const double* cle;    // dev [B][seglen] or nullptr
+  const double* sk;     // dev [B]
+  int B;
+  int64_t N, seg0, seglen, k0, k1;
+  int const_var;
+};
+
+// per-launch scratch (device)
+struct Scratch {
+  double* sqrtu;   // [B]  sqrt(1/v)
+  double* halflogv;// [B]  0.5*log(v)
+  double* uconst;  // [B]  1/v
+  double* dw;      // [B][seglen] d/v      (general path)
+  double* uu;      // [B][seglen] 1/v      (general path)
+  double2* part;   // [nhyp][NC][B*nk] partial log-sum-exp (max, sum)
+  double* bgabs;   // [B*nk] polynomial-only log Bayes factor (no sumlogsigma) or nullptr
+  int NC;          // number of template chunks
+  int gchunk;      // templates per chunk
+  int KT;          // samples per thread of the fast kernel
+};
+
+struct LaunchStats { int64_t launches = 0; };
+
+cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
+                                 double* d_raw, cudaStream_t s, LaunchStats* st);
+cudaError_t launch_plan_orthonormalise(const double* d_raw, const double* d_qb, int G, int W, int WP, int P,
+                                       double* d_hat, double* d_Kg, cudaStream_t s, LaunchStats* st);
+
+cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st);
+// polynomial-only factor for interior constant-variance samples (fast path)
+cudaError_t launch_bgproj(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s, LaunchStats* st);
+// fused window kernel, log-sum-exp mode (detector) -- interior, constant variance
+cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
+                                   LaunchStats* st);
+// fused window kernel, full output mode for one hypothesis: out[gorig][B? no: single curve][nk]
+cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
+                                    double sumlogsigma, double* d_out, cudaStream_t s, LaunchStats* st);
+// general path (truncated windows at the series ends, or per-sample variance)
+cudaError_t launch_window_general_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, bool edges_only,
+                                      cudaStream_t s, LaunchStats* st);
+cudaError_t launch_window_general_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
+                                       bool edges_only, double sumlogsigma, double* d_out,
+                                       cudaStream_t s, LaunchStats* st);
+// merge partial log-sum-exps, combine hypotheses into log odds
+cudaError_t launch_combine(const PlanView& pv, const SeriesView& sv, const Scratch& sc, int noisepoly,
+                           double* d_lnO, double* d_marg, cudaStream_t s, LaunchStats* st);
+
+cudaError_t launch_pe_grid(int kind, int reverse, const double* d_cts, const double* d_clc, int L,
+                           const double* d_params, const double* d_logprior, int64_t G, int P,
+                           const double* d_polyms, double sigma, int margbackground, double* d_post,
+                           cudaStream_t s, LaunchStats* st);
+
+cudaError_t launch_logtrapz(const double* d_lx, const double* d_t, int64_t n, int64_t m, double* d_out,
+                            cudaStream_t s, LaunchStats* st);
+
+cudaError_t launch_threshold_edges(const double* d_lnO, int64_t n, double thresh, int64_t* d_starts,
+                                   int64_t* d_stops, int* d_counts, int cap, cudaStream_t s, LaunchStats* st);
+cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int nsegs, double* d_maxval,
+                              int64_t* d_maxidx, cudaStream_t s, LaunchStats* st);
+
+cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
+
+size_t fast_smem_bytes(int W, int gchunk, int KT);
+int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out);
+
+}  // namespace bfl

@@ -1,0 +1,250 @@
+"""``OddsRatioDetector`` -- drop-in mirror of ``bayesflare/finder/find.py:465-1019``.
+
+``oddsratio()`` builds every hypothesis (flare signal; polynomial, impulse, exponential
+decay / rise, step noise models) into ONE device plan and runs the fused window kernel: the
+per-grid-point likelihoods, their trapezium marginalisation and the noise-model combination
+all happen on the GPU and only the log odds come back.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+
+from . import _lib
+from .bayes import background_models, estimate_sigma, hypothesis_from_model, window_times
+from .models import Expdecay, Flare, Impulse, Step
+
+__all__ = ["OddsRatioDetector", "contiguous_regions"]
+
+
+def contiguous_regions(condition):
+    """Start/stop indices (half open) of the runs of True in ``condition`` (find.py:15-52)."""
+    condition = np.asarray(condition)
+    d = np.diff(condition)
+    idx, = d.nonzero()
+    idx = idx + 1
+    if condition[0]:
+        idx = np.r_[0, idx]
+    if condition[-1]:
+        idx = np.r_[idx, condition.size]
+    idx.shape = (-1, 2)
+    return idx
+
+
+class OddsRatioDetector:
+    """Log odds ratio of "flare + polynomial background" against a set of noise models for
+    every sample, plus thresholding.  Same constructor and setters as the reference
+    (find.py:541-739); ``device`` is an extra optional keyword."""
+
+    def __init__(self,
+                 lightcurve,
+                 bglen=55,
+                 bgorder=4,
+                 nsinusoids=0,
+                 noiseestmethod='powerspectrum',
+                 psestfrac=0.5,
+                 tvsigma=1.0,
+                 flareparams={'taugauss': (0, 1.5 * 60 * 60, 10), 'tauexp': (0.5 * 60 * 60, 3. * 60 * 60, 10)},
+                 noisepoly=True,
+                 noiseimpulse=True,
+                 noiseimpulseparams={'t0': (np.inf,)},
+                 noiseexpdecay=True,
+                 noiseexpdecayparams={'tauexp': (0.0, 0.25 * 60 * 60, 3)},
+                 noiseexpdecaywithreverse=True,
+                 noisestep=False,
+                 noisestepparams={'t0': (np.inf,)},
+                 ignoreedges=True,
+                 device=None):
+        self.lightcurve = deepcopy(lightcurve)
+        self.bglen = bglen
+        self.bgorder = bgorder
+        self.nsinusoids = nsinusoids
+        self.device = device
+        self._plan = None
+        self._plan_key = None
+        self.set_flare_params(flareparams=flareparams)
+        self.set_noise_est_method(noiseestmethod=noiseestmethod, psestfrac=psestfrac, tvsigma=tvsigma)
+        self.set_noise_poly(noisepoly=noisepoly)
+        self.set_noise_impulse(noiseimpulse=noiseimpulse, noiseimpulseparams=noiseimpulseparams)
+        self.set_noise_expdecay(noiseexpdecay=noiseexpdecay, noiseexpdecayparams=noiseexpdecayparams,
+                                withreverse=noiseexpdecaywithreverse)
+        self.set_noise_step(noisestep=noisestep, noisestepparams=noisestepparams)
+        self.set_ignore_edges(ignoreedges=ignoreedges)
+
+    # ---- configuration (find.py:578-739).  Unlike the reference the caller's dictionaries are
+    # copied, not mutated (the reference writes 'amp'/'t0' into its mutable default arguments).
+    def set_ignore_edges(self, ignoreedges=True):
+        self.ignoreedges = ignoreedges
+
+    def set_flare_params(self, flareparams={'taugauss': (0, 1.5 * 60 * 60, 10), 'tauexp': (0.5 * 60 * 60, 3. * 60 * 60, 10)}):
+        if 'taugauss' not in flareparams:
+            raise ValueError("Error... dictionary has no parameter 'taugauss'")
+        if 'tauexp' not in flareparams:
+            raise ValueError("Error... dictionary has no parameter 'tauexp'")
+        flareparams = dict(flareparams)
+        flareparams.setdefault('t0', (np.inf,))
+        flareparams['amp'] = (1.,)
+        self.flareparams = flareparams
+        self._plan_key = None
+
+    def set_noise_est_method(self, noiseestmethod='powerspectrum', psestfrac=0.5, tvsigma=1.0):
+        self.psestfrac = None
+        self.tvsigma = None
+        self.noiseestmethod = noiseestmethod
+        if noiseestmethod == 'powerspectrum':
+            self.psestfrac = psestfrac
+        elif noiseestmethod == 'tailveto':
+            self.tvsigma = tvsigma
+        else:
+            print("Noise estimation method %s not recognised" % noiseestmethod)
+
+    def set_noise_poly(self, noisepoly=True):
+        self.noisepoly = noisepoly
+
+    def set_noise_impulse(self, noiseimpulse=True, noiseimpulseparams={'t0': (np.inf,)}, positive=False):
+        self.noiseimpulse = noiseimpulse
+        if 't0' not in noiseimpulseparams:
+            raise ValueError("Error... no 't0' value set")
+        noiseimpulseparams = dict(noiseimpulseparams)
+        noiseimpulseparams['amp'] = (1.,)
+        self.noiseimpulseparams = noiseimpulseparams
+        self.noiseimpulsepositive = positive
+        self._plan_key = None
+
+    def set_noise_expdecay(self, noiseexpdecay=True, noiseexpdecayparams={'tauexp': (0.0, 0.25 * 60 * 60, 3)},
+                           withreverse=True):
+        self.noiseexpdecay = noiseexpdecay
+        self.noiseexpdecaywithreverse = withreverse
+        if 'tauexp' not in noiseexpdecayparams:
+            raise ValueError("Error... 'tauexp' parameter range not given.")
+        noiseexpdecayparams = dict(noiseexpdecayparams)
+        noiseexpdecayparams.setdefault('t0', (np.inf,))
+        noiseexpdecayparams['amp'] = (1.,)
+        self.noiseexpdecayparams = noiseexpdecayparams
+        self._plan_key = None
+
+    def set_noise_step(self, noisestep=False, noisestepparams={'t0': (np.inf,)}):
+        self.noisestep = noisestep
+        if 't0' not in noisestepparams:
+            raise ValueError("Error... 't0' parameter range not set.")
+        noisestepparams = dict(noisestepparams)
+        noisestepparams['amp'] = (1.,)
+        self.noisestepparams = noisestepparams
+        self._plan_key = None
+
+    # ---- the engine ------------------------------------------------------------------------
+    def hypotheses(self, cts):
+        """The models of find.py:762-843 in the reference's order: signal first, then the noise
+        models [impulse, expdecay, reversed expdecay, step] (the polynomial-only model is a flag)."""
+        models = [(Flare(cts, amp=1, paramranges=self.flareparams), True)]
+        if self.noiseimpulse:
+            models.append((Impulse(cts, amp=1, paramranges=self.noiseimpulseparams), bool(self.noiseimpulsepositive)))
+        if self.noiseexpdecay:
+            models.append((Expdecay(cts, amp=1, paramranges=self.noiseexpdecayparams), True))
+            if self.noiseexpdecaywithreverse:
+                models.append((Expdecay(cts, amp=1, reverse=True, paramranges=self.noiseexpdecayparams), True))
+        if self.noisestep:
+            models.append((Step(cts, amp=1, paramranges=self.noisestepparams), False))
+        return models
+
+    def plan(self, cts=None):
+        """Build (or reuse) the device plan for this configuration and time base."""
+        cts = self.lightcurve.cts if cts is None else cts
+        cts = np.asarray(cts, dtype=float)
+        if self.bglen is None or self.nsinusoids != 0:
+            raise NotImplementedError("the whole-series background (bglen=None / nsinusoids != 0) is not part of "
+                                      "the sliding-window GPU path")
+        if self.bglen % 2 == 0:
+            print("Error... Background length (bglen) must be an odd number")
+            return None
+        models = self.hypotheses(cts)
+        mts = np.asarray(window_times(cts, self.bglen, models[0][0].t0), dtype=float)
+        key = (self.bglen, self.bgorder, mts.tobytes(), repr(sorted(self.flareparams.items())),
+               self.noiseimpulse, repr(sorted(self.noiseimpulseparams.items())), self.noiseimpulsepositive,
+               self.noiseexpdecay, repr(sorted(self.noiseexpdecayparams.items())), self.noiseexpdecaywithreverse,
+               self.noisestep, repr(sorted(self.noisestepparams.items())))
+        if self._plan is not None and key == self._plan_key:
+            return self._plan
+        if self._plan is not None:
+            self._plan.close()
+        ctx = _lib.default_context(self.device)
+        hyps = [hypothesis_from_model(m, mts, hr) for m, hr in models]
+        self._plan = _lib.Plan(ctx, self.bglen, background_models(self.bglen, self.bgorder), mts, hyps)
+        self._plan_key = key
+        self.ngrid_eval = int(sum(np.isfinite(h["logprior"]).sum() for h in hyps)) + (1 if self.noisepoly else 0)
+        self.ngrid_nominal = int(sum(h["logprior"].size for h in hyps)) + (1 if self.noisepoly else 0)
+        return self._plan
+
+    def noise_sigma(self, lightcurve=None):
+        lc = self.lightcurve if lightcurve is None else lightcurve
+        return estimate_sigma(lc, self.bglen, self.bgorder, self.noiseestmethod, self.psestfrac, self.tvsigma)
+
+    def oddsratio(self):
+        """Time series of the log odds ratio (find.py:741-864).  Returns ``(lnO, ts)`` with
+        ``lnO`` a list of floats, as the reference does."""
+        lc = self.lightcurve
+        plan = self.plan()
+        if plan is None:
+            return None
+        sk = self.noise_sigma()
+        if sk is None:
+            return None
+        N = len(lc.cts)
+        cle = np.asarray(lc.cle, dtype=float)
+        lnO = plan.detector_odds(lc.clc, cle if np.any(cle != 0) else None, sk, noisepoly=self.noisepoly)
+        nnoise = plan.nhyp - 1 + (1 if self.noisepoly else 0)
+        if nnoise == 0:
+            # no noise models: signal versus Gaussian noise (find.py:859-862) carries the
+            # sum-of-log-sigma constant of general.pyx:216-221
+            noisevar = sk ** 2 + cle ** 2
+            lnO = lnO + float(np.sum(np.log(np.sqrt(noisevar))))
+        if self.ignoreedges and self.bglen is not None:
+            h = int(self.bglen / 2)
+            sel = slice(h, N - h)
+        else:
+            sel = slice(0, N)
+        return list(lnO[sel]), np.copy(lc.cts[sel])
+
+    def oddsratio_batch(self, clc, sk=None, cle=None):
+        """Extension: log odds for a batch ``clc[B, N]`` of light curves that share this detector's
+        time base and configuration, in one launch.  ``sk[B]`` are the noise sigmas (estimated per
+        curve when omitted).  Returns an array ``[B, N']`` (edges dropped when ``ignoreedges``)."""
+        clc = np.atleast_2d(np.asarray(clc, dtype=float))
+        B, N = clc.shape
+        plan = self.plan()
+        if sk is None:
+            from .lightcurve import Lightcurve
+            sk = np.array([self.noise_sigma(Lightcurve(cts=self.lightcurve.cts, clc=clc[b],
+                                                       cle=None if cle is None else cle[b])) for b in range(B)])
+        lnO = plan.detector_odds(clc, cle, sk, noisepoly=self.noisepoly)
+        if self.ignoreedges:
+            h = int(self.bglen / 2)
+            lnO = lnO[:, h:N - h]
+        return lnO
+
+    # ---- post-processing (find.py:866-1019) -----------------------------------------------
+    def impulse_excluder(self, lnO, ts, exclusionwidth=5):
+        """Mask +-``exclusionwidth`` samples around M-shaped impulse artefacts (find.py:866-912)."""
+        lnOa = np.copy(lnO)
+        n = len(lnOa)
+        keep = np.ones(n, dtype=bool)
+        for idx in np.arange(n)[lnOa < -5.]:
+            if 1 < idx < n - 2:
+                c1 = lnOa[idx - 1] > 0 and lnOa[idx - 2] > 0 and lnOa[idx - 2] < lnOa[idx - 1]
+                c2 = lnOa[idx + 1] > 0 and lnOa[idx + 2] > 0 and lnOa[idx + 2] < lnOa[idx + 1]
+                if c1 and c2:
+                    keep[max(idx - exclusionwidth, 0):min(idx + exclusionwidth, n - 1)] = False
+        return lnOa[keep], np.copy(ts)[keep]
+
+    def thresholder(self, lnO, thresh, expand=0, returnmax=True):
+        """Regions where ``lnO > thresh``, optionally expanded and merged, with the maximum of each
+        (find.py:915-1019).  The scan, merge and per-region argmax run through ``bfl_threshold``."""
+        segs, mv, mi = _lib.threshold(_lib.default_context(self.device), np.asarray(lnO, dtype=float), thresh, expand)
+        if expand > 0 and len(segs) == 1:
+            flarelist = [[int(segs[0, 0]), int(segs[0, 1])]]     # the reference returns a list here (find.py:961)
+        else:
+            flarelist = [(int(a), int(b)) for a, b in segs]
+        if returnmax:
+            return flarelist, len(flarelist), [(float(v), int(i)) for v, i in zip(mv, mi)]
+        return flarelist, len(flarelist)

@@ -1,0 +1,152 @@
+/* bfl.h -- C ABI of libbfl.so: the B200 (sm_100a) sliding-window Bayesian odds-ratio engine.
+ *
+ * This is the drop-in boundary for BayesFlare's native layer.  The reference's native
+ * boundary is Python -> Cython cpdef functions taking NumPy arrays
+ * (bayesflare/stats/general.pyx:143-147, :249-252, :315, :576, :610) -> C
+ * (bayesflare/stats/log_marg_amp_full.h:12-14).  Each entry point below names the
+ * reference interface it replaces.  Plain pointers and sizes only; no torch / NumPy types.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, <0 = bfl_status; the message of the
+ *     last failure on the calling thread is available from bfl_last_error();
+ *   - nothing throws or aborts across the ABI;
+ *   - "host" pointers are caller-owned C-contiguous float64 buffers (NumPy arrays);
+ *     "dev" pointers are device allocations the caller owns (e.g. a torch tensor's
+ *     data_ptr()) and work is enqueued on the context's stream without synchronising;
+ *   - a context is bound to one device and one stream and is not thread-safe;
+ *   - masked grid points (log prior = -inf) yield -inf exactly as the reference does.
+ */
+#ifndef BFL_H
+#define BFL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFL_VERSION 100
+
+typedef enum {
+  BFL_OK = 0,
+  BFL_ERR_ARG = -1,         /* bad argument (the reference prints and returns None) */
+  BFL_ERR_CUDA = -2,        /* a CUDA runtime call failed; see bfl_last_error() */
+  BFL_ERR_OOM = -3,         /* host or device allocation failed */
+  BFL_ERR_UNSUPPORTED = -4, /* valid request outside what this build covers */
+  BFL_ERR_NODEVICE = -5     /* no CUDA device: there is deliberately no CPU fallback */
+} bfl_status;
+
+/* template generators of bayesflare/models/model.py, evaluated on device */
+typedef enum {
+  BFL_MODEL_FLARE = 0,    /* Flare.model    model.py:197-252   params (t0, tauexp, taugauss, amp) */
+  BFL_MODEL_EXPDECAY = 1, /* Expdecay.model model.py:560-607   params (t0, amp, tauexp, -)       */
+  BFL_MODEL_IMPULSE = 2,  /* Impulse.model  model.py:694-736   params (t0, amp, -, -)            */
+  BFL_MODEL_STEP = 3,     /* Step.model     model.py:943-982   params (t0, amp, -, -)            */
+  BFL_MODEL_TRANSIT = 4,  /* Transit.model  model.py:387-436   params (t0, sigmag, tauf, amp)    */
+  BFL_MODEL_GAUSSIAN = 5, /* Gaussian.model model.py:814-858   params (t0, sigma, amp, -)        */
+  BFL_MODEL_TABLE = 6     /* caller-supplied templates (any other Model subclass)               */
+} bfl_model_kind;
+
+typedef struct bfl_ctx bfl_ctx;   /* device + stream + scratch memory */
+typedef struct bfl_plan bfl_plan; /* a set of hypotheses on one window time base */
+
+/* One hypothesis = one Model + its parameter grid (ravelled in C order, as
+ * np.unravel_index does in bayes.py:348) + how its amplitude is marginalised. */
+typedef struct {
+  int32_t kind;          /* bfl_model_kind */
+  int32_t reverse;       /* Model.reverse (Flare / Expdecay) */
+  int32_t halfrange;     /* 1: amplitude in [0,inf) (lastHalfRange=1), 0: (-inf,inf) */
+  int32_t ngrid;         /* number of grid points */
+  const double* params;  /* host [ngrid][4], kind-specific order above; t0 = +inf means "window centre" */
+  const double* logprior;/* host [ngrid]: Model.prior() + log amplitude prior (bayes.py:284-288,352-356); -inf masks */
+  const double* logweight;/* host [ngrid]: log of the product trapezium weight of the grid point (general.pyx:576-607) */
+  const double* table;   /* host [ngrid][W] templates when kind == BFL_MODEL_TABLE, else NULL */
+} bfl_hypothesis;
+
+/* ---- library / context -------------------------------------------------------------- */
+int bfl_version(void);
+const char* bfl_last_error(void);
+int bfl_device_count(void);
+
+/* device < 0 selects the current device.  stream == NULL creates a private stream;
+ * otherwise `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+int bfl_ctx_create(int device, void* stream, bfl_ctx** ctx);
+int bfl_ctx_destroy(bfl_ctx* ctx);
+int bfl_ctx_sync(bfl_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t bfl_ctx_launch_count(const bfl_ctx* ctx);
+
+/* ---- plan: templates + per-grid-point constants, built on device --------------------
+ * Replaces the model/prior/cross-term set-up loop of Bayes.bayes_factors_marg_poly_bgd
+ * (bayes.py:292-307 bgmodels, :347-356 templates, :367-393 model cross terms).
+ *   W        bglen (odd), P = bgorder+1 (1..6)
+ *   bgmodels host [P][W]  background basis, as the caller's NumPy computed it (bayes.py:297,307)
+ *   mts      host [W]     time stamps the templates are evaluated on (bayes.py:261-276)     */
+int bfl_plan_create(bfl_ctx* ctx, int W, int P, const double* bgmodels, const double* mts,
+                    const bfl_hypothesis* hyps, int nhyp, bfl_plan** plan);
+int bfl_plan_destroy(bfl_plan* plan);
+/* device-generated templates of hypothesis ihyp -> host out[ngrid][W] (masked rows are zero).
+ * Equivalent of Model.__call__(q, ts=mts).clc (model.py:133-153). */
+int bfl_plan_templates(bfl_plan* plan, int ihyp, double* out);
+
+/* ---- Bayes.bayes_factors_marg_poly_bgd / _only (bayes.py:153-563) --------------------
+ * replaces log_marg_amp_full_model / _2Dmodel / _background (general.pyx:143-365) and
+ * log_marg_amp_full_C (log_marg_amp_full.c:3-68) for every sample and grid point.
+ *   clc, cle host [N]  (cle may be NULL = zeros); sk noise sigma (bayes.py:239-245)
+ *   sumlogsigma        sum_i log sqrt(sk^2+cle_i^2) as general.pyx:216-221 computes it
+ *   out_lnB   host [ngrid][N] or NULL: lnBmargAmp of hypothesis ihyp (prior included)
+ *   out_bg    host [N] or NULL: the polynomial-only factor (lnBmargBackground)           */
+int bfl_window_lnB(bfl_ctx* ctx, bfl_plan* plan, int ihyp, const double* clc, const double* cle,
+                   double sk, int64_t N, double sumlogsigma, double* out_lnB, double* out_bg);
+
+/* ---- OddsRatioDetector.oddsratio (find.py:741-864), fused -----------------------------
+ * hypothesis 0 of the plan is the signal; hypotheses 1.. are noise models; noisepoly adds
+ * the polynomial-only noise model first, as find.py:774-782 does.  For a batch of B light
+ * curves on the same time base:
+ *   clc, cle host [B][N] (cle NULL = zeros), sk host [B]
+ *   out_lnO  host [B][N]   log odds for EVERY sample (callers drop the first/last W/2 when
+ *                          ignoreedges, find.py:846-851)
+ *   out_marg host [(nhyp+1)][B][N] or NULL: marginalised log Bayes factor of each hypothesis
+ *                          (index nhyp = polynomial-only), without the sumlogsigma constant  */
+int bfl_detector_odds(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double* clc, const double* cle,
+                      const double* sk, int32_t B, int64_t N, double* out_lnO, double* out_marg);
+
+/* Same, device resident and asynchronous on the context's stream.  Supports time chunks:
+ * the buffers hold samples [seg0, seg0+seglen) of series of true length N; log odds are
+ * produced for samples [k0, k1) (k0-W/2 >= seg0 or seg0 == 0; likewise at the end) and
+ * written to out_lnO[b*(k1-k0) + (k-k0)].
+ *   d_clc, d_cle dev [B][seglen] (d_cle NULL = zeros; const_var = 1 promises cle is constant
+ *   per curve so the translation-invariant fast path is taken), d_sk dev [B]               */
+int bfl_detector_odds_dev(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double* d_clc,
+                          const double* d_cle, int const_var, const double* d_sk, int32_t B, int64_t N,
+                          int64_t seg0, int64_t seglen, int64_t k0, int64_t k1, double* d_lnO);
+
+/* ---- OddsRatioDetector.thresholder (find.py:915-1019) on device ----------------------
+ * contiguous regions of lnO > thresh, expanded by `expand` and merged; per region the
+ * maximum and its index.  lnO host [n]; segs host [max_segs][2] (start, stop), maxval /
+ * maxidx host [max_segs]; *nsegs receives the number found (may exceed max_segs).       */
+int bfl_threshold(bfl_ctx* ctx, const double* lnO, int64_t n, double thresh, int32_t expand,
+                  int64_t* segs, double* maxval, int64_t* maxidx, int32_t max_segs, int32_t* nsegs);
+
+/* ---- ParameterEstimationGrid.calculate_posterior (bayes.py:912-1055) -----------------
+ * replaces log_likelihood_marg_background (general.pyx:610-656) ->
+ * log_marg_amp_except_final_C (log_marg_amp_full.c:71-134) when margbackground != 0 and
+ * log_likelihood_ratio (general.pyx:659-691) otherwise.  One light-curve chunk:
+ *   cts, clc host [L]; grid: kind + params host [G][4] (+ logprior host [G]); P = bgorder+1
+ *   polyms host [P][L]: linspace(0,1,L)**p as the caller's NumPy computed it (bayes.py:984-988)
+ *   out_post host [G] = log likelihood + log prior                                      */
+int bfl_pe_grid(bfl_ctx* ctx, int32_t kind, int32_t reverse, const double* cts, const double* clc,
+                int64_t L, const double* params, const double* logprior, int64_t G, int32_t P,
+                const double* polyms, double sigma, int32_t margbackground, double* out_post);
+
+/* ---- logtrapz (general.pyx:576-607) over the leading axis of lx[n][m] -> out[m] ------ */
+int bfl_logtrapz(bfl_ctx* ctx, const double* lx, const double* t, int64_t n, int64_t m, double* out);
+
+/* ---- measurement helper: sustained FP64 FMA throughput (TFLOP/s) of this device,
+ * the denominator of the window kernel's roofline (not in MEASURED_PEAKS.json).        */
+int bfl_fp64_peak_probe(bfl_ctx* ctx, int32_t iters, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFL_H */

@@ -1,0 +1,323 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI / the drop-in Python API,
+against (a) golden fixtures generated from the reference and (b) the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): |delta| <= 1e-9 * max(1, |ref|) on log odds / log Bayes
+factors with an identical -inf pattern; detection indices bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import assert_logodds_close, load_golden
+import bayesflare_b200 as bf
+from bayesflare_b200 import _lib, bayes as bbayes
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+DT = 1765.55929
+TOL = 1e-9
+
+
+def _lc(cts, clc, cle=None):
+    return bf.Lightcurve(cts=cts, clc=clc, cle=cle)
+
+
+def _force_sk(monkeypatch, sk):
+    monkeypatch.setattr(bbayes, "estimate_sigma", lambda *a, **k: sk)
+
+
+KAT = {
+    "flare": (bf.Flare, {}, {"t0": (np.inf,), "taugauss": (0, 5400, 4), "tauexp": (1800, 10800, 4), "amp": (1.,)}, True),
+    "impulse": (bf.Impulse, {}, {"t0": (0, 54 * DT, 55), "amp": (1.,)}, False),
+    "impulse1": (bf.Impulse, {}, {"t0": (np.inf,), "amp": (1.,)}, False),
+    "expdecay": (bf.Expdecay, {}, {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True),
+    "expdecay_rev": (bf.Expdecay, {"reverse": True}, {"t0": (np.inf,), "tauexp": (0.0, 900, 3), "amp": (1.,)}, True),
+    "step": (bf.Step, {}, {"t0": (np.inf,), "amp": (1.,)}, False),
+    "transit": (bf.Transit, {}, {"t0": (np.inf,), "sigmag": (1800, 7200, 3), "tauf": (0, 7200, 4), "amp": (1.,)}, True),
+    "flare_full": (bf.Flare, {}, {"t0": (np.inf,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3), "amp": (1.,)}, False),
+}
+
+
+def test_device_present_and_native_library_loaded():
+    assert _lib.load().bfl_device_count() >= 1
+    ctx = _lib.default_context()
+    tf, ms = _lib.fp64_peak(ctx, 512)
+    assert tf > 1.0, "FP64 probe reports %.2f TFLOP/s" % tf
+    assert ctx.launches > 0
+
+
+@pytest.mark.parametrize("name", sorted(KAT))
+def test_templates_generated_on_device(name):
+    cls, kw, pr, hr = KAT[name]
+    ts = np.arange(400) * DT
+    m = cls(ts, paramranges=dict(pr), **kw)
+    mts = bbayes.window_times(ts, 55, m.t0)
+    plan = _lib.Plan(_lib.default_context(), 55, bbayes.background_models(55, 4), mts,
+                     [bbayes.hypothesis_from_model(m, mts, hr)])
+    dev = plan.templates(0)
+    lp = m.grid_logprior()
+    for q in range(dev.shape[0]):
+        host = m(q, ts=mts).clc if np.isfinite(lp[q]) else np.zeros(55)
+        np.testing.assert_allclose(dev[q], host, rtol=4e-16, atol=1e-300, err_msg="%s q=%d" % (name, q))
+        assert np.array_equal(dev[q] == 0, host == 0)
+
+
+@pytest.mark.parametrize("name", sorted(KAT))
+def test_kat200_general_variance_path_vs_reference(name, monkeypatch):
+    """Per-sample variance (cle varies): every sample goes through the reference-order path."""
+    g = load_golden("kat200")
+    _force_sk(monkeypatch, float(g["sk"]))
+    cls, kw, pr, hr = KAT[name]
+    lc = _lc(g["cts"], g["clc"], g["cle"])
+    B = bf.Bayes(lc, cls(lc.cts, amp=1, paramranges=dict(pr), **kw))
+    B.bayes_factors_marg_poly_bgd(halfrange=hr)
+    assert_logodds_close(B.lnBmargAmp, g["ref_lnB_" + name], TOL, name)
+    assert_logodds_close(B.marginalise_full().lnBmargAmp, g["ref_marg_" + name], TOL, name + " marg")
+    if name == "flare":
+        assert_logodds_close(B.bayes_factors_marg_poly_bgd_only(), g["ref_bgonly"], TOL, "bgonly")
+        assert abs(B.noise_ev - float(g["ref_noise_ev"])) <= 1e-9 * abs(float(g["ref_noise_ev"]))
+        assert abs(B.lnBmargAmp[0, 3, 0, 0, 100] - (-19.112936560497506)) < 1e-9
+
+
+def test_kat200_other_window_and_order(monkeypatch):
+    g = load_golden("kat200")
+    _force_sk(monkeypatch, float(g["sk"]))
+    lc = _lc(g["cts"], g["clc"], g["cle"])
+    B = bf.Bayes(lc, bf.Flare(lc.cts, amp=1, paramranges=dict(KAT["flare"][2])))
+    B.bayes_factors_marg_poly_bgd(bglen=21, bgorder=2)
+    assert_logodds_close(B.lnBmargAmp, g["ref_lnB_flare_w21_o2"], TOL, "w21 o2")
+    assert_logodds_close(B.bayes_factors_marg_poly_bgd_only(bglen=21, bgorder=2), g["ref_bgonly_w21_o2"], TOL, "bg w21")
+
+
+@pytest.mark.parametrize("name", ["flare", "impulse", "expdecay_rev", "step", "transit", "flare_full"])
+@pytest.mark.parametrize("bglen,bgorder", [(55, 4), (21, 2), (55, 0), (33, 5)])
+def test_constant_variance_fast_path_vs_oracle(name, bglen, bgorder, monkeypatch):
+    """cle constant: interior samples take the translation-invariant fast path, the first/last
+    bglen/2 samples the truncated-window path; all N samples are compared."""
+    rng = np.random.default_rng(42)
+    N = 700
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal(N) * 1.3 + orc.flare_model(ts, ts[300], 9., 1500., 4000.) \
+        + 2.0 * np.sin(2 * np.pi * ts / (2.2 * 86400.))
+    clc -= np.median(clc)
+    cle = np.full(N, 0.4)
+    sk = 1.234
+    _force_sk(monkeypatch, sk)
+    cls, kw, pr, hr = KAT[name]
+    pr = dict(pr)
+    if name == "impulse":
+        pr["t0"] = (0, (bglen - 1) * DT, bglen)
+    lc = _lc(ts, clc, cle)
+    B = bf.Bayes(lc, cls(ts, amp=1, paramranges=pr, **kw))
+    B.bayes_factors_marg_poly_bgd(bglen=bglen, bgorder=bgorder, halfrange=hr)
+    ref, _, refbg = orc.bayes_factors(clc, cle, ts, cls(ts).mtype, pr, sk, bglen=bglen, bgorder=bgorder,
+                                      halfrange=hr, reverse=kw.get("reverse", False), with_background=True)
+    assert_logodds_close(B.lnBmargAmp, ref, TOL, "%s W%d o%d" % (name, bglen, bgorder))
+    assert_logodds_close(B.bayes_factors_marg_poly_bgd_only(bglen=bglen, bgorder=bgorder), refbg, TOL, "bg")
+
+
+@pytest.mark.parametrize("meth", ["powerspectrum", "tailveto"])
+def test_detector_default_vs_reference(meth):
+    g = load_golden("detector")
+    det = bf.OddsRatioDetector(_lc(g["a_cts"], g["a_clc"]), noiseestmethod=meth)
+    lnO, ts = det.oddsratio()
+    assert isinstance(lnO, list) and len(lnO) == len(g["a_clc"]) - 54
+    assert_logodds_close(lnO, g["ref_a_lnO_" + meth], TOL, meth)
+    np.testing.assert_array_equal(ts, g["a_cts"][27:-27])
+    fl, n, mx = det.thresholder(lnO, 16.5, expand=1)
+    assert np.array_equal(np.array(fl, dtype=np.int64).reshape(-1, 2), g["ref_a_segs_" + meth])
+    assert np.array_equal(np.array([m[1] for m in mx], dtype=float), g["ref_a_max_" + meth][:, 1])
+    assert det.ngrid_eval == 93 and det.ngrid_nominal == 108
+
+
+def test_detector_scripts_configuration_and_options_vs_reference():
+    g = load_golden("detector")
+    det = bf.OddsRatioDetector(_lc(g["b_cts"], g["b_clc"]), bglen=55, bgorder=4, noiseestmethod="tailveto", tvsigma=1.0,
+                               noiseimpulseparams={"t0": (0, 54 * DT, 55)})
+    lnO, ts = det.oddsratio()
+    assert_logodds_close(lnO, g["ref_b_lnO"], TOL, "scripts detector")
+    fl, n, mx = det.thresholder(lnO, 10.0, expand=2)
+    assert np.array_equal(np.array(fl, dtype=np.int64).reshape(-1, 2), g["ref_b_segs"])
+    assert np.array_equal(np.array([m[1] for m in mx], dtype=float), g["ref_b_max"][:, 1])
+    assert det.ngrid_eval == 147
+    det = bf.OddsRatioDetector(_lc(g["c_cts"], g["c_clc"]), noiseestmethod="tailveto", noisestep=True, ignoreedges=False)
+    det.set_noise_impulse(noiseimpulse=True, noiseimpulseparams={"t0": (np.inf,)}, positive=True)
+    lnO, ts = det.oddsratio()
+    assert len(lnO) == len(g["c_clc"])
+    assert_logodds_close(lnO, g["ref_c_lnO"], TOL, "step + edges + positive impulse")
+
+
+def test_config1_single_long_cadence_quarter_vs_reference():
+    """BASELINE config 1: N=4400, default detector; SURVEY 8(c) end-to-end known answer."""
+    g = load_golden("config1")
+    for meth, kat in (("powerspectrum", 18.343102610670442), ("tailveto", 19.80097630627027)):
+        det = bf.OddsRatioDetector(_lc(g["cts"], g["clc"]), noiseestmethod=meth)
+        lnO, ts = det.oddsratio()
+        assert len(lnO) == 4346
+        assert_logodds_close(lnO, g["ref_lnO_" + meth], TOL, "config1 " + meth)
+        assert int(np.argmax(lnO)) == 2174 and abs(max(lnO) - kat) < 1e-9
+        fl, n, mx = det.thresholder(lnO, 16.5, expand=1)
+        assert [tuple(s) for s in fl] == [(2171, 2176)] and n == 1 and mx[0][1] == 2174
+        above = np.nonzero(np.array(lnO) > 16.5)[0]
+        np.testing.assert_array_equal(above, np.nonzero(g["ref_lnO_" + meth] > 16.5)[0])   # bit-exact detections
+
+
+def test_config2_short_cadence_vs_reference():
+    g = load_golden("shortcad")
+    det = bf.OddsRatioDetector(_lc(g["cts"], g["clc"]))
+    lnO, ts = det.oddsratio()
+    assert_logodds_close(lnO, g["ref_lnO"], TOL, "short cadence")
+    for thr in (5.0, 16.5):
+        np.testing.assert_array_equal(np.nonzero(np.array(lnO) > thr)[0], np.nonzero(g["ref_lnO"] > thr)[0])
+
+
+def test_detector_no_noise_models_and_varying_errors_vs_oracle():
+    rng = np.random.default_rng(5)
+    N = 500
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal(N) + orc.flare_model(ts, ts[250], 7., 900., 3500.)
+    cle = 0.2 + 0.1 * rng.random(N)
+    det = bf.OddsRatioDetector(_lc(ts, clc, cle), noiseestmethod="tailveto", noisepoly=False, noiseimpulse=False,
+                               noiseexpdecay=False)
+    lnO, _ = det.oddsratio()
+    ref, _ = orc.oddsratio(clc, cle, ts, noiseestmethod="tailveto", noisepoly=False, noiseimpulse=False, noiseexpdecay=False)
+    assert_logodds_close(lnO, ref, TOL, "no noise models")
+    det = bf.OddsRatioDetector(_lc(ts, clc, cle), noiseestmethod="tailveto", ignoreedges=False)
+    lnO, _ = det.oddsratio()
+    ref, _ = orc.oddsratio(clc, cle, ts, noiseestmethod="tailveto", ignoreedges=False)
+    assert_logodds_close(lnO, ref, TOL, "varying cle detector")
+
+
+def test_batch_equals_single_and_oracle():
+    rng = np.random.default_rng(9)
+    B, N = 6, 900
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal((B, N)) * rng.uniform(0.5, 3, (B, 1))
+    for b in range(B):
+        clc[b] += orc.flare_model(ts, ts[100 + 120 * b], 5. + 3 * b, 800., 2500.)
+    det = bf.OddsRatioDetector(_lc(ts, clc[0]), noiseestmethod="tailveto")
+    sk = np.array([det.noise_sigma(_lc(ts, clc[b])) for b in range(B)])
+    batch = det.oddsratio_batch(clc, sk=sk)
+    assert batch.shape == (B, N - 54)
+    for b in range(B):
+        single, _ = bf.OddsRatioDetector(_lc(ts, clc[b]), noiseestmethod="tailveto").oddsratio()
+        np.testing.assert_array_equal(batch[b], single)
+        ref, _ = orc.oddsratio(clc[b], np.zeros(N), ts, noiseestmethod="tailveto")
+        assert_logodds_close(batch[b], ref, TOL, "batch %d" % b)
+
+
+def test_time_chunks_with_halos_equal_whole_series():
+    """Config-2 mechanism: a long series cut into chunks, each staged with a W/2 halo, gives
+    bit-identical log odds to the un-chunked run (device-resident API)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    N = 5000
+    ts = np.arange(N) * 58.84876
+    clc = rng.standard_normal(N) + orc.flare_model(ts, ts[2600], 9., 200., 900.)
+    det = bf.OddsRatioDetector(_lc(ts, clc))
+    plan = det.plan()
+    sk = det.noise_sigma()
+    whole = plan.detector_odds(clc, None, sk)
+    dev = torch.device("cuda:0")
+    d_sk = torch.tensor([sk], dtype=torch.float64, device=dev)
+    out = np.empty(N)
+    H = 27
+    bounds = [0, 1300, 2617, 3999, N]
+    for k0, k1 in zip(bounds[:-1], bounds[1:]):
+        s0, s1 = max(0, k0 - H), min(N, k1 + H)
+        d_seg = torch.tensor(clc[s0:s1], dtype=torch.float64, device=dev)
+        d_out = torch.empty(k1 - k0, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        plan.detector_odds_dev(d_seg.data_ptr(), 0, True, d_sk.data_ptr(), 1, N, s0, s1 - s0, k0, k1, d_out.data_ptr())
+        plan.ctx.sync()
+        out[k0:k1] = d_out.cpu().numpy()
+    np.testing.assert_array_equal(out, whole)
+
+
+def test_threshold_on_device_vs_oracle_random():
+    rng = np.random.default_rng(13)
+    ctx = _lib.default_context()
+    for n, thr, expand in [(50, 0.5, 0), (1000, 1.0, 0), (1000, 1.0, 3), (5000, 2.0, 1), (300, -9.0, 2), (300, 9.0, 2),
+                           (4000, 1.5, 7)]:
+        x = np.cumsum(rng.standard_normal(n)) * 0.3 + rng.standard_normal(n)
+        segs, mv, mi = _lib.threshold(ctx, x, thr, expand)
+        rs, rn, rm = orc.thresholder(x, thr, expand=expand)
+        assert [tuple(map(int, s)) for s in segs] == [tuple(map(int, s)) for s in rs]
+        assert [int(i) for i in mi] == [int(m[1]) for m in rm]
+        assert [float(v) for v in mv] == [float(m[0]) for m in rm]
+
+
+def test_logtrapz_on_device():
+    rng = np.random.default_rng(17)
+    lx = rng.uniform(-40, 5, (9, 37))
+    lx[3, 5] = -np.inf
+    lx[:, 7] = -np.inf
+    t = np.sort(rng.uniform(0, 10, 9))
+    got = _lib.logtrapz_axis0(_lib.default_context(), lx, t)
+    ref = np.array([orc.logtrapz(lx[:, j], t) for j in range(37)])
+    assert_logodds_close(got, ref, 1e-13, "logtrapz")
+
+
+def test_parameter_estimation_grid_vs_reference():
+    """BASELINE config 4 (reduced grid): scripts/parameter_estimation_example.py."""
+    g = load_golden("pegrid")
+    lc = _lc(g["cts"], g["clc"])
+    t0, idx, a = float(g["t0"]), int(g["idxt0"]), g["amprange"]
+    for bgorder in (3, 4, 2):
+        pe = bf.ParameterEstimationGrid('flare', lc)
+        assert abs(pe.noiseSigma - float(g["ref_sigma"])) < 1e-12
+        pe.lightcurve_chunk(idx, 55)
+        pe.set_grid(ranges={'taugauss': (0., 3600., 12), 'tauexp': (0., 12000., 10), 'amp': (a[0], a[1], int(a[2])), 't0': (t0,)})
+        pe.calculate_posterior(bgorder=bgorder)
+        assert pe.posterior.shape == (1, 10, 12, 9)
+        assert_logodds_close(pe.posterior, g["ref_post_o%d" % bgorder], TOL, "pe bgorder %d" % bgorder)
+        if bgorder == 3:
+            pe.marginalise_all()
+            for p in ("taugauss", "tauexp", "amp"):
+                np.testing.assert_allclose(pe.margposteriors[p], g["ref_margpost_" + p], rtol=1e-8, atol=1e-300)
+            mp, mpar = pe.maximum_posterior()
+            assert abs(mp - float(g["ref_maxpost"])) <= 1e-9 * abs(float(g["ref_maxpost"]))
+            np.testing.assert_array_equal([mpar[p] for p in ("t0", "tauexp", "taugauss", "amp")], g["ref_maxpost_params"])
+            assert abs(pe.maximum_posterior_snr() - float(g["ref_snr"])) < 1e-9
+    pe = bf.ParameterEstimationGrid('flare', lc)
+    pe.lightcurve_chunk(idx, 55)
+    pe.set_grid(ranges={'taugauss': (0., 3600., 6), 'tauexp': (0., 12000., 5), 'amp': (a[0], a[1], int(a[2])), 't0': (t0,)})
+    pe.calculate_posterior(margbackground=False)
+    assert_logodds_close(pe.posterior, g["ref_post_nobg"], TOL, "pe no background")
+
+
+def test_dense_grid_property_and_oracle_subset():
+    """BASELINE config 4 detector part: 64x64 tau grid (templates span many chunks).  Checked by
+    (i) the oracle on a short curve, (ii) refinement consistency at full length."""
+    rng = np.random.default_rng(21)
+    N = 260
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal(N) + orc.flare_model(ts, ts[130], 10., 1200., 3000.)
+    fp = {"taugauss": (0, 5400, 64), "tauexp": (1800, 10800, 64)}
+    det = bf.OddsRatioDetector(_lc(ts, clc), noiseestmethod="tailveto", flareparams=fp)
+    lnO, _ = det.oddsratio()
+    ref, _ = orc.oddsratio(clc, np.zeros(N), ts, noiseestmethod="tailveto", flareparams=fp)
+    assert_logodds_close(lnO, ref, TOL, "64x64 grid")
+
+
+def test_error_conventions(capsys):
+    ts = np.arange(300) * DT
+    lc = _lc(ts, np.random.default_rng(0).standard_normal(300))
+    B = bf.Bayes(lc, bf.Flare(ts, paramranges={"t0": (np.inf,), "taugauss": (0, 5400, 2), "tauexp": (1800, 10800, 2), "amp": (1.,)}))
+    assert B.bayes_factors_marg_poly_bgd(bglen=54) is None            # bayes.py:229-233
+    assert "must be an odd number" in capsys.readouterr().out
+    assert B.bayes_factors_marg_poly_bgd(noiseestmethod="nope") is None   # bayes.py:243-245
+    assert "Noise estimation method" in capsys.readouterr().out
+    with pytest.raises(_lib.BflError):
+        _lib.Plan(_lib.default_context(), 54, bbayes.background_models(54, 4), ts[:54], [])
+    # non-finite data -> -inf, as log_marg_amp_full.c:20,25
+    clc = lc.clc.copy()
+    clc[150] = np.nan
+    B = bf.Bayes(_lc(ts, clc, np.linspace(0.1, 0.2, 300)), bf.Step(ts, paramranges={"t0": (np.inf,), "amp": (1.,)}))
+    import bayesflare_b200.bayes as bb
+    old = bb.estimate_sigma
+    bb.estimate_sigma = lambda *a, **k: 1.0
+    try:
+        B.bayes_factors_marg_poly_bgd(halfrange=False)
+    finally:
+        bb.estimate_sigma = old
+    assert np.all(B.lnBmargAmp[0, 0, 150 - 27:150 + 28] == -np.inf)
+    assert np.all(np.isfinite(B.lnBmargAmp[0, 0, :150 - 27]))
