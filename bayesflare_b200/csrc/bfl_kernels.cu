@@ -199,7 +199,7 @@ __global__ void k_prep_scalars(const double* __restrict__ sk, const double* __re
   if (b >= B) return;
   const double s = sk[b];
   const double e = cle ? cle[(size_t)b * seglen] : 0.0;
-  const double v = s * s + e * e;   // bayes.py:312
+  const double v = __dadd_rn(__dmul_rn(s, s), __dmul_rn(e, e));   // bayes.py:312, no FMA contraction
   const double u = 1.0 / v;
   uconst[b] = u;
   sqrtu[b] = sqrt(u);
@@ -214,9 +214,9 @@ __global__ void k_prep_whiten(const double* __restrict__ clc, const double* __re
   const int b = (int)(i / seglen);
   const double s = sk[b];
   const double e = cle ? cle[i] : 0.0;
-  const double v = s * s + e * e;
-  dw[i] = clc[i] / v;   // bayes.py:403
-  uu[i] = 1.0 / v;
+  const double v = __dadd_rn(__dmul_rn(s, s), __dmul_rn(e, e));   // sk**2 + cle**2 as NumPy rounds it
+  dw[i] = __ddiv_rn(clc[i], v);   // bayes.py:403
+  uu[i] = v;   // the variance itself: the general path divides, as bayes.py:321-327 does
 }
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st) {
@@ -260,7 +260,7 @@ constexpr int FAST_TPB = 128;
 template <int WT, int KT>
 __device__ __forceinline__ void correlate_reg(const double* __restrict__ t, const double* win, double (&z)[KT]) {
   constexpr int NPAIR = (WT + 1) / 2;
-  constexpr int NACC = (KT >= 4) ? 1 : (4 / KT);
+  constexpr int NACC = 2;   // same summation order for every KT: results do not depend on the tiling
   double acc[KT][NACC];
 #pragma unroll
   for (int j = 0; j < KT; j++)
@@ -670,7 +670,7 @@ __device__ __forceinline__ double signal_logL(const BgElim<P>& e, const double (
 
 struct GenArgs {
   const double* dw;     // [B][seglen]
-  const double* uu;     // [B][seglen]
+  const double* uu;     // [B][seglen] noise variance v
   int64_t seglen, N, seg0, k0, k1;
   int B, tiles_per_curve, edges_only, tpb;
   const double* raw; const double* lp; const double* lw; const int* gorig;
@@ -699,7 +699,7 @@ __global__ void k_window_general(const GenArgs a) {
   double* sbg = smem;                       // [P][WP]
   double* sbb = sbg + P * WP;               // [NPAIR][WP]
   double* stm = sbb + NPAIR * WP;           // [gchunk][WP]
-  double* swu = stm + (size_t)a.gchunk * WP;// [W][TPB]  1/v window, transposed
+  double* swu = stm + (size_t)a.gchunk * WP;// [W][TPB]  noise-variance window, transposed
   double* swd = swu + (size_t)W * TPB;      // [W][TPB]  d/v window, transposed
 
   for (int i = tid; i < P * WP; i += TPB) sbg[i] = a.bg[i];
@@ -746,7 +746,7 @@ __global__ void k_window_general(const GenArgs a) {
 #pragma unroll
       for (int q = p; q < P; q++) {
         const double* bbp = sbb + pq * WP + w0;
-        M[p][q] = pairwise_np(n, [&](int i) { return mul_(bbp[i], swu[(w0 + i) * TPB + tid]); });
+        M[p][q] = pairwise_np(n, [&](int i) { return div_(bbp[i], swu[(w0 + i) * TPB + tid]); });
         pq++;
       }
       const double* bp = sbg + p * WP + w0;
@@ -769,12 +769,12 @@ __global__ void k_window_general(const GenArgs a) {
     for (int g = lo; g < hi; g++) {
       const double* m = stm + (size_t)(g - gb) * WP + w0;
       // model x model (bayes.py:367-377), model x background (bayes.py:380-393)
-      const double mm = pairwise_np(n, [&](int i) { return mul_(mul_(m[i], m[i]), swu[(w0 + i) * TPB + tid]); });
+      const double mm = pairwise_np(n, [&](int i) { return div_(mul_(m[i], m[i]), swu[(w0 + i) * TPB + tid]); });
       double mdbg[P];
 #pragma unroll
       for (int p = 0; p < P; p++) {
         const double* bp = sbg + p * WP + w0;
-        mdbg[p] = pairwise_np(n, [&](int i) { return mul_(mul_(bp[i], m[i]), swu[(w0 + i) * TPB + tid]); });
+        mdbg[p] = pairwise_np(n, [&](int i) { return div_(mul_(bp[i], m[i]), swu[(w0 + i) * TPB + tid]); });
       }
       // data x model (general.pyx:210)
       double dm = 0.0;

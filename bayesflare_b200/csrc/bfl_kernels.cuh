@@ -50,7 +50,7 @@ struct Scratch {
   double* halflogv;// [B]  0.5*log(v)
   double* uconst;  // [B]  1/v
   double* dw;      // [B][seglen] d/v      (general path)
-  double* uu;      // [B][seglen] 1/v      (general path)
+  double* uu;      // [B][seglen] v        (general path)
   double2* part;   // [nhyp][NC][B*nk] partial log-sum-exp (max, sum)
   double* bgabs;   // [B*nk] polynomial-only log Bayes factor (no sumlogsigma) or nullptr
   int NC;          // number of template chunks

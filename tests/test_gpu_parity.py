@@ -199,7 +199,9 @@ def test_batch_equals_single_and_oracle():
     assert batch.shape == (B, N - 54)
     for b in range(B):
         single, _ = bf.OddsRatioDetector(_lc(ts, clc[b]), noiseestmethod="tailveto").oddsratio()
-        np.testing.assert_array_equal(batch[b], single)
+        # tiling (samples per thread, template chunks) depends on the batch size, so the
+        # log-sum-exp merge order may differ: identical to rounding, not bit for bit
+        np.testing.assert_allclose(batch[b], single, rtol=0, atol=2e-13)
         ref, _ = orc.oddsratio(clc[b], np.zeros(N), ts, noiseestmethod="tailveto")
         assert_logodds_close(batch[b], ref, TOL, "batch %d" % b)
 
@@ -229,7 +231,12 @@ def test_time_chunks_with_halos_equal_whole_series():
         plan.detector_odds_dev(d_seg.data_ptr(), 0, True, d_sk.data_ptr(), 1, N, s0, s1 - s0, k0, k1, d_out.data_ptr())
         plan.ctx.sync()
         out[k0:k1] = d_out.cpu().numpy()
-    np.testing.assert_array_equal(out, whole)
+    fin = np.isfinite(whole)
+    assert np.array_equal(np.isfinite(out), fin)
+    np.testing.assert_allclose(out[fin], whole[fin], rtol=0, atol=2e-13)
+    ref, _ = orc.oddsratio(clc, np.zeros(N), ts, ignoreedges=False)
+    assert_logodds_close(out[27:-27], ref[27:-27], TOL, "chunked short cadence")
+    np.testing.assert_array_equal(np.nonzero(out[27:-27] > 16.5)[0], np.nonzero(ref[27:-27] > 16.5)[0])
 
 
 def test_threshold_on_device_vs_oracle_random():
@@ -308,16 +315,13 @@ def test_error_conventions(capsys):
     assert "Noise estimation method" in capsys.readouterr().out
     with pytest.raises(_lib.BflError):
         _lib.Plan(_lib.default_context(), 54, bbayes.background_models(54, 4), ts[:54], [])
-    # non-finite data -> -inf, as log_marg_amp_full.c:20,25
+    # non-finite data -> -inf, as log_marg_amp_full.c:20,25 (reference-order path)
     clc = lc.clc.copy()
     clc[150] = np.nan
-    B = bf.Bayes(_lc(ts, clc, np.linspace(0.1, 0.2, 300)), bf.Step(ts, paramranges={"t0": (np.inf,), "amp": (1.,)}))
-    import bayesflare_b200.bayes as bb
-    old = bb.estimate_sigma
-    bb.estimate_sigma = lambda *a, **k: 1.0
-    try:
-        B.bayes_factors_marg_poly_bgd(halfrange=False)
-    finally:
-        bb.estimate_sigma = old
-    assert np.all(B.lnBmargAmp[0, 0, 150 - 27:150 + 28] == -np.inf)
-    assert np.all(np.isfinite(B.lnBmargAmp[0, 0, :150 - 27]))
+    m = bf.Step(ts, paramranges={"t0": (np.inf,), "amp": (1.,)})
+    mts = bbayes.window_times(ts, 55, m.t0)
+    plan = _lib.Plan(_lib.default_context(), 55, bbayes.background_models(55, 4), mts,
+                     [bbayes.hypothesis_from_model(m, mts, False)])
+    lnB, bg = plan.window_lnB(0, clc, np.linspace(0.1, 0.2, 300), 1.0, 0.0, want_bg=True)
+    assert np.all(lnB[0, 150 - 27:150 + 28] == -np.inf) and np.all(bg[150 - 27:150 + 28] == -np.inf)
+    assert np.all(np.isfinite(lnB[0, :150 - 27])) and np.all(np.isfinite(bg[150 + 28:]))
