@@ -40,13 +40,17 @@ SIGNATURES = {
     "bfl_ctx_destroy": (C.c_int, [C.c_void_p]),
     "bfl_ctx_sync": (C.c_int, [C.c_void_p]),
     "bfl_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "bfl_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "bfl_ctx_window_time": (C.c_int, [C.c_void_p, _dp, _i64p]),
+    "bfl_count_regions_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
     "bfl_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(Hypothesis), C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "bfl_plan_destroy": (C.c_int, [C.c_void_p]),
     "bfl_plan_templates": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "bfl_window_lnB": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int64, C.c_double,
                                  _dp, _dp]),
-    "bfl_detector_odds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int32, C.c_int64, _dp, _dp]),
+    "bfl_detector_odds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int32, C.c_int64, C.c_int64,
+                                    C.c_int64, _dp, _dp]),
     "bfl_detector_odds_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_void_p]),
@@ -107,6 +111,18 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.bfl_ctx_launch_count(self.handle))
+
+    def set_timing(self, enable=True):
+        check(self.lib.bfl_ctx_set_timing(self.handle, 1 if enable else 0))
+
+    def window_time(self):
+        """(summed ms, launches) of the fused window kernel since the last call."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(self.lib.bfl_ctx_window_time(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def count_regions_dev(self, d_lnO, B, n, thresh, d_counts):
+        check(self.lib.bfl_count_regions_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_counts))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -185,7 +201,8 @@ class Plan:
                                       float(sk), N, float(sumlogsigma), ptr(out), ptr(bg)))
         return out, bg
 
-    def detector_odds(self, clc, cle, sk, noisepoly=True, want_marg=False):
+    def detector_odds(self, clc, cle, sk, noisepoly=True, want_marg=False, k0=0, k1=None):
+        """Log odds for samples [k0, k1) of every curve (default: all N samples)."""
         clc = f64(clc)
         single = clc.ndim == 1
         clc = np.atleast_2d(clc)
@@ -194,10 +211,11 @@ class Plan:
         sk = f64(np.atleast_1d(sk))
         if sk.size != B or (cle is not None and cle.shape != clc.shape):
             raise ValueError("batch shapes of clc, cle and sk do not agree")
-        lnO = np.empty((B, N))
-        marg = np.empty((self.nhyp + 1, B, N)) if want_marg else None
+        k1 = N if k1 is None else int(k1)
+        lnO = np.empty((B, k1 - k0))
+        marg = np.empty((self.nhyp + 1, B, k1 - k0)) if want_marg else None
         check(self.lib.bfl_detector_odds(self.ctx.handle, self.handle, 1 if noisepoly else 0, ptr(clc), ptr(cle),
-                                         ptr(sk), B, N, ptr(lnO), ptr(marg)))
+                                         ptr(sk), B, N, int(k0), k1, ptr(lnO), ptr(marg)))
         if single:
             lnO = lnO[0]
             marg = None if marg is None else marg[:, 0]

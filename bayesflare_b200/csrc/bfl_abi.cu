@@ -38,6 +38,9 @@ struct bfl_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   LaunchStats stats;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tfree; // recycled event pairs
   std::map<std::string, std::pair<void*, size_t>> pool;   // grow-only named device buffers
 
   int get(const char* name, size_t bytes, void** out) {
@@ -109,6 +112,8 @@ int bfl_ctx_destroy(bfl_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->pool)
     if (kv.second.first) cudaFree(kv.second.first);
+  for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& pr : c->tfree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return BFL_OK;
@@ -121,6 +126,35 @@ int bfl_ctx_sync(bfl_ctx* c) {
 }
 
 int64_t bfl_ctx_launch_count(const bfl_ctx* c) { return c ? c->stats.launches : 0; }
+
+int bfl_ctx_set_timing(bfl_ctx* c, int enable) {
+  if (!c) return fail(BFL_ERR_ARG, "null context");
+  c->timing = enable != 0;
+  return BFL_OK;
+}
+
+int bfl_ctx_window_time(bfl_ctx* c, double* total_ms, int64_t* launches) {
+  if (!c || !total_ms || !launches) return fail(BFL_ERR_ARG, "null argument to bfl_ctx_window_time");
+  CK(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (auto& pr : c->tev) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+    c->tfree.push_back(pr);
+  }
+  *total_ms = tot;
+  *launches = (int64_t)c->tev.size();
+  c->tev.clear();
+  return BFL_OK;
+}
+
+static int timing_begin(bfl_ctx* c, std::pair<cudaEvent_t, cudaEvent_t>& pr) {
+  if (!c->tfree.empty()) { pr = c->tfree.back(); c->tfree.pop_back(); }
+  else { CK(cudaEventCreate(&pr.first)); CK(cudaEventCreate(&pr.second)); }
+  CK(cudaEventRecord(pr.first, c->stream));
+  return BFL_OK;
+}
 
 // --------------------------------------------------------------------------------------
 static int plan_alloc(bfl_plan* p, size_t bytes, void** out) {
@@ -351,7 +385,10 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   cudaStream_t s = c->stream;
   CK(launch_prep(sv, sc, need_general, s, &c->stats));
   if (sv.const_var) {
+    std::pair<cudaEvent_t, cudaEvent_t> pr;
+    if (c->timing && (rc = timing_begin(c, pr))) return rc;
     CK(launch_window_fast_lse(pv, sv, sc, s, &c->stats));
+    if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
     if (need_bg) CK(launch_bgproj(pv, sv, sc, s, &c->stats));
     if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));
   } else {
@@ -380,9 +417,11 @@ static bool rows_constant(const double* a, int B, int64_t N) {
 }
 
 int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc, const double* cle,
-                      const double* sk, int32_t B, int64_t N, double* out_lnO, double* out_marg) {
+                      const double* sk, int32_t B, int64_t N, int64_t k0, int64_t k1, double* out_lnO,
+                      double* out_marg) {
   if (!c || !p || !clc || !sk || !out_lnO) return fail(BFL_ERR_ARG, "null argument to bfl_detector_odds");
   if (B < 1 || N < 1) return fail(BFL_ERR_ARG, "empty batch");
+  if (k0 < 0 || k1 > N || k0 >= k1) return fail(BFL_ERR_ARG, "bad sample range");
   CK(cudaSetDevice(c->device));
   const bool cv = (cle == nullptr) || rows_constant(cle, B, N);
   const size_t nb = sizeof(double) * (size_t)B * N;
@@ -391,16 +430,17 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
   if ((rc = c->get("in_clc", nb, &d_clc))) return rc;
   if (cle && (rc = c->get("in_cle", nb, &d_cle))) return rc;
   if ((rc = c->get("in_sk", sizeof(double) * (size_t)B, &d_sk))) return rc;
-  if ((rc = c->get("out_lnO", nb, &d_lnO))) return rc;
-  if (out_marg && (rc = c->get("out_marg", nb * (size_t)(p->pv.nhyp + 1), &d_marg))) return rc;
+  const size_t nbo = sizeof(double) * (size_t)B * (size_t)(k1 - k0);
+  if ((rc = c->get("out_lnO", nbo, &d_lnO))) return rc;
+  if (out_marg && (rc = c->get("out_marg", nbo * (size_t)(p->pv.nhyp + 1), &d_marg))) return rc;
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(d_clc, clc, nb, cudaMemcpyHostToDevice, s));
   if (cle) CK(cudaMemcpyAsync(d_cle, cle, nb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
-  SeriesView sv{(const double*)d_clc, (const double*)d_cle, (const double*)d_sk, B, N, 0, N, 0, N, cv ? 1 : 0};
+  SeriesView sv{(const double*)d_clc, (const double*)d_cle, (const double*)d_sk, B, N, 0, N, k0, k1, cv ? 1 : 0};
   if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO, (double*)d_marg))) return rc;
-  CK(cudaMemcpyAsync(out_lnO, d_lnO, nb, cudaMemcpyDeviceToHost, s));
-  if (out_marg) CK(cudaMemcpyAsync(out_marg, d_marg, nb * (size_t)(p->pv.nhyp + 1), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out_lnO, d_lnO, nbo, cudaMemcpyDeviceToHost, s));
+  if (out_marg) CK(cudaMemcpyAsync(out_marg, d_marg, nbo * (size_t)(p->pv.nhyp + 1), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return BFL_OK;
 }
@@ -453,6 +493,14 @@ int bfl_window_lnB(bfl_ctx* c, bfl_plan* p, int ihyp, const double* clc, const d
   CK(cudaStreamSynchronize(s));
   if (out_bg)
     for (int64_t i = 0; i < N; i++) out_bg[i] += sumlogsigma;   // general.pyx:363
+  return BFL_OK;
+}
+
+int bfl_count_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n, double thresh, int64_t* d_counts) {
+  if (!c || !d_lnO || !d_counts || B < 1 || n < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_count_regions_dev");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)B, c->stream));
+  CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, c->stream, &c->stats));
   return BFL_OK;
 }
 

@@ -50,12 +50,61 @@ __device__ __forceinline__ double phi_half(double z) {
   return log(erfcx(t));
 }
 
-// online log-sum-exp: m = running maximum, s = sum exp(x_i - m)
+#include "phi_table.inc"
+
+// phi(z) from the piecewise degree-6 table (tools/gen_phi_table.py; |error| < 2e-14), `tab` is the
+// shared-memory copy laid out [coefficient][interval].  Branch-free on [-12.06, 9.06]; beyond it
+// erfc(-z/sqrt2) = 2 to 1e-19 (z large) or the erfcx form is used (z very negative, rare).
+__device__ __forceinline__ double phi_half_tab(double z, const double* __restrict__ tab) {
+  const double s = fma(z, BFL_PHI_INVH, -(BFL_PHI_ZMIN) * BFL_PHI_INVH);
+  int k = __double2int_rn(s);
+  k = min(max(k, 0), BFL_PHI_NI - 1);
+  const double x = s - (double)k;
+  double v = tab[6 * BFL_PHI_NI + k];
+  v = fma(v, x, tab[5 * BFL_PHI_NI + k]);
+  v = fma(v, x, tab[4 * BFL_PHI_NI + k]);
+  v = fma(v, x, tab[3 * BFL_PHI_NI + k]);
+  v = fma(v, x, tab[2 * BFL_PHI_NI + k]);
+  v = fma(v, x, tab[1 * BFL_PHI_NI + k]);
+  v = fma(v, x, tab[k]);
+  if (z > 9.0625) v = fma(0.5 * z, z, BFL_LN2);
+  else if (z < -12.0625) v = log(erfcx(-z * 0.70710678118654752440));
+  return v;
+}
+
+// e^d for d <= 0 (NaN propagates): magic-number range reduction, degree-11 polynomial on
+// |r| <= ln2/2 (relative error < 7e-15), exponent patched in with integer arithmetic.
+__device__ __forceinline__ double exp_nonpos(double d) {
+  d = (d < -700.0) ? -700.0 : d;
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+  const double t = fma(d, 1.4426950408889634074, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  double r = fma(nf, -6.93147180369123816490e-01, d);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 2.50521083854417187751e-08;      // 1/11!
+  p = fma(p, r, 2.75573192239858906526e-07);  // 1/10!
+  p = fma(p, r, 2.75573192239858906526e-06);  // 1/9!
+  p = fma(p, r, 2.48015873015873015873e-05);  // 1/8!
+  p = fma(p, r, 1.98412698412698412698e-04);  // 1/7!
+  p = fma(p, r, 1.38888888888888888889e-03);  // 1/6!
+  p = fma(p, r, 8.33333333333333333333e-03);  // 1/5!
+  p = fma(p, r, 4.16666666666666666667e-02);  // 1/4!
+  p = fma(p, r, 1.66666666666666666667e-01);  // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// online log-sum-exp, branch-free: m = running maximum (starts at LSE_EMPTY), s = sum exp(x_i - m)
+#define LSE_EMPTY (-1.0e300)
 __device__ __forceinline__ void lse_push(double& m, double& s, double x) {
-  if (x == neg_inf()) return;
   const double d = x - m;
-  const double e = exp(-fabs(d));
-  if (d > 0.0) { s = fma(s, e, 1.0); m = x; } else { s += e; }
+  const double e = exp_nonpos(-fabs(d));
+  const bool up = d > 0.0;
+  s = up ? fma(s, e, 1.0) : (s + e);
+  m = up ? x : m;
 }
 
 __device__ __forceinline__ double logplus_dev(double x, double y) {
@@ -306,6 +355,7 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
   double* sdata = smem;                          // [ndata] (padded to even)
   double* stmpl = smem + ((ndata + 1) & ~1);     // [gchunk][WP]
   double* sK = stmpl + (size_t)a.gchunk * WP;    // [gchunk]  Kg + lp (+ lw)
+  double* sphi = sK + ((a.gchunk + 1) & ~1);     // [(DEG+1) * NI] phi(z) table
 
   // ---- stage the light-curve tile + halo (coalesced), pre-scaled by sqrt(1/v) ----
   {
@@ -328,6 +378,7 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
       if (MODE == 0) k += a.lw[gb + i];
       sK[i] = k;
     }
+    for (int i = tid; i < (BFL_PHI_DEG + 1) * BFL_PHI_NI; i += FAST_TPB) sphi[i] = BFL_PHI_TAB[i];
   }
   __syncthreads();
 
@@ -358,7 +409,7 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
     const double hc = (half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
     double mx[KT], sm[KT];
 #pragma unroll
-    for (int j = 0; j < KT; j++) { mx[j] = neg_inf(); sm[j] = 0.0; }
+    for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
 
     for (int g = lo; g < hi; g++) {
       const double* t = stmpl + (size_t)(g - gb) * WP;
@@ -376,7 +427,7 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
       const double kg = sK[g - gb];
 #pragma unroll
       for (int j = 0; j < KT; j++) {
-        const double val = kg + (half ? phi_half(z[j]) : 0.5 * z[j] * z[j]);
+        const double val = kg + (half ? phi_half_tab(z[j], sphi) : 0.5 * z[j] * z[j]);
         if (MODE == 0) {
           lse_push(mx[j], sm[j], val);
         } else if (valid[j]) {
@@ -397,7 +448,8 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
 size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int WP = W + 1;
   const int ndata = FAST_TPB * KT + 2 * (W / 2) + 2;
-  return sizeof(double) * (size_t)(((ndata + 1) & ~1) + (size_t)gchunk * WP + gchunk);
+  return sizeof(double) * (size_t)(((ndata + 1) & ~1) + (size_t)gchunk * WP + ((gchunk + 1) & ~1) +
+                                   (BFL_PHI_DEG + 1) * BFL_PHI_NI);
 }
 
 // choose samples-per-thread and the template chunk so that the grid covers the chip
@@ -765,7 +817,7 @@ __global__ void k_window_general(const GenArgs a) {
     const int lo = max(gb, a.hyp_begin[h]), hi = min(ge, a.hyp_begin[h + 1]);
     if (lo >= hi) continue;
     const bool half = a.hyp_half[h] != 0;
-    double mx = neg_inf(), sm = 0.0;
+    double mx = LSE_EMPTY, sm = 0.0;
     for (int g = lo; g < hi; g++) {
       const double* m = stm + (size_t)(g - gb) * WP + w0;
       // model x model (bayes.py:367-377), model x background (bayes.py:380-393)
@@ -868,13 +920,16 @@ __global__ void k_combine(const CombArgs a) {
     double M = neg_inf();
     const int c0 = a.hyp_begin[h] / a.gchunk;
     const int c1 = (a.hyp_begin[h + 1] > a.hyp_begin[h]) ? (a.hyp_begin[h + 1] - 1) / a.gchunk : c0 - 1;
-    for (int c = c0; c <= c1; c++) M = fmax(M, a.part[(size_t)(h * a.NC + c) * a.BK + i].x);
+    for (int c = c0; c <= c1; c++) {
+      const double2 p = a.part[(size_t)(h * a.NC + c) * a.BK + i];
+      if (p.y > 0.0 || isnan(p.y)) M = fmax(M, p.x);
+    }
     double S = 0.0;
     bool nan_ = false;
     for (int c = c0; c <= c1; c++) {
       const double2 p = a.part[(size_t)(h * a.NC + c) * a.BK + i];
       if (isnan(p.x) || isnan(p.y)) nan_ = true;
-      if (p.x != neg_inf()) S += p.y * exp(p.x - M);
+      if (p.y > 0.0) S += p.y * exp(p.x - M);
     }
     rel[h] = nan_ ? nan("") : ((S > 0.0) ? M + log(S) : neg_inf());
   }
@@ -1186,6 +1241,25 @@ cudaError_t launch_threshold_edges(const double* d_lnO, int64_t n, double thresh
                                    int64_t* d_stops, int* d_counts, int cap, cudaStream_t s, LaunchStats* st) {
   if (n <= 0) return cudaSuccess;
   k_threshold_edges<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_lnO, n, thresh, d_starts, d_stops, d_counts, cap);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+// number of region starts per curve (a start = above threshold and predecessor not above)
+__global__ void k_count_regions(const double* __restrict__ lnO, int B, int64_t n, double thresh,
+                                unsigned long long* counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * B) return;
+  const int64_t k = i % n;
+  if (!(lnO[i] > thresh)) return;
+  if (k > 0 && lnO[i - 1] > thresh) return;
+  atomicAdd(&counts[i / n], 1ULL);
+}
+
+cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
+                                 cudaStream_t s, LaunchStats* st) {
+  const int64_t tot = n * B;
+  k_count_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts);
   st->launches++;
   return cudaGetLastError();
 }

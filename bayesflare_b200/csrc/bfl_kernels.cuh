@@ -97,6 +97,8 @@ cudaError_t launch_threshold_edges(const double* d_lnO, int64_t n, double thresh
 cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int nsegs, double* d_maxval,
                               int64_t* d_maxidx, cudaStream_t s, LaunchStats* st);
 
+cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
+                                 cudaStream_t s, LaunchStats* st);
 cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
 
 size_t fast_smem_bytes(int W, int gchunk, int KT);

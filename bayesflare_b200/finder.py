@@ -192,19 +192,18 @@ class OddsRatioDetector:
             return None
         N = len(lc.cts)
         cle = np.asarray(lc.cle, dtype=float)
-        lnO = plan.detector_odds(lc.clc, cle if np.any(cle != 0) else None, sk, noisepoly=self.noisepoly)
+        # ignoreedges (find.py:846-851): the first/last bglen/2 samples are dropped, so they are
+        # never computed (they would take the slow truncated-window path)
+        h = int(self.bglen / 2) if self.ignoreedges else 0
+        lnO = plan.detector_odds(lc.clc, cle if np.any(cle != 0) else None, sk, noisepoly=self.noisepoly,
+                                 k0=h, k1=N - h)
         nnoise = plan.nhyp - 1 + (1 if self.noisepoly else 0)
         if nnoise == 0:
             # no noise models: signal versus Gaussian noise (find.py:859-862) carries the
             # sum-of-log-sigma constant of general.pyx:216-221
             noisevar = sk ** 2 + cle ** 2
             lnO = lnO + float(np.sum(np.log(np.sqrt(noisevar))))
-        if self.ignoreedges and self.bglen is not None:
-            h = int(self.bglen / 2)
-            sel = slice(h, N - h)
-        else:
-            sel = slice(0, N)
-        return list(lnO[sel]), np.copy(lc.cts[sel])
+        return list(lnO), np.copy(lc.cts[h:N - h])
 
     def oddsratio_batch(self, clc, sk=None, cle=None):
         """Extension: log odds for a batch ``clc[B, N]`` of light curves that share this detector's
@@ -217,11 +216,8 @@ class OddsRatioDetector:
             from .lightcurve import Lightcurve
             sk = np.array([self.noise_sigma(Lightcurve(cts=self.lightcurve.cts, clc=clc[b],
                                                        cle=None if cle is None else cle[b])) for b in range(B)])
-        lnO = plan.detector_odds(clc, cle, sk, noisepoly=self.noisepoly)
-        if self.ignoreedges:
-            h = int(self.bglen / 2)
-            lnO = lnO[:, h:N - h]
-        return lnO
+        h = int(self.bglen / 2) if self.ignoreedges else 0
+        return plan.detector_odds(clc, cle, sk, noisepoly=self.noisepoly, k0=h, k1=N - h)
 
     # ---- post-processing (find.py:866-1019) -----------------------------------------------
     def impulse_excluder(self, lnO, ts, exclusionwidth=5):

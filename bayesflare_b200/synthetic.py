@@ -1,0 +1,46 @@
+"""Synthetic Kepler-like light curves (no FITS data is available offline).
+
+Follows the recipe the reference's own scripts use to simulate data
+(``scripts/flare_detection_efficiency.py:262-289, 321-335, 416-434, 483-487``): white Gaussian noise
+on the long- or short-cadence time base, an optional low-frequency sinusoid ("coloured" case),
+one injected flare per curve with tau_gauss <= tau_exp and a uniform signal-to-noise ratio, then
+median subtraction as ``Lightcurve.dcoffset`` does (data/data.py:271-277)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .models import Flare
+
+DT_LONG = 1765.55929       # s
+DT_SHORT = 58.84876        # s
+
+__all__ = ["DT_LONG", "DT_SHORT", "simulate_batch"]
+
+
+def simulate_batch(B, N, dt=DT_LONG, seed=0, nstd=1.0, sinusoid_amp=0.0, inject=True, snr_range=(0., 50.)):
+    """Return ``(cts[N], clc[B, N], truth)``; curve ``i`` uses ``default_rng(1000*seed + i)``."""
+    cts = np.arange(N, dtype=np.float64) * dt
+    clc = np.empty((B, N))
+    truth = {"idx": np.zeros(B, dtype=np.int64), "snr": np.zeros(B), "taugauss": np.zeros(B), "tauexp": np.zeros(B)}
+    flare = Flare(cts, amp=1.)
+    h = 27
+    for i in range(B):
+        rng = np.random.default_rng(1000 * seed + i)
+        x = nstd * rng.standard_normal(N)
+        if sinusoid_amp > 0:
+            amp = rng.uniform(0, sinusoid_amp) * nstd
+            f = rng.uniform(1. / (31. * 86400.), 1. / (2. * 86400.))
+            x += amp * np.sin(2 * np.pi * f * cts + rng.uniform(0, 2 * np.pi))
+        if inject:
+            idx = int(rng.integers(h, N - h - 1))
+            te = rng.uniform(1800., 10800.)
+            tg = rng.uniform(0., 5400.)
+            while tg > te:
+                tg = rng.uniform(0., 5400.)
+            snr = rng.uniform(*snr_range)
+            lo, hi = max(0, idx - 4 * h), min(N, idx + 12 * h)     # the template is negligible outside
+            inj = flare.model({"t0": cts[idx], "amp": 1., "taugauss": tg, "tauexp": te}, ts=cts[lo:hi])
+            x[lo:hi] += inj * (snr * nstd / np.sqrt(np.sum(inj ** 2)))
+            truth["idx"][i], truth["snr"][i], truth["taugauss"][i], truth["tauexp"][i] = idx, snr, tg, te
+        clc[i] = x - np.median(x)
+    return cts, clc, truth

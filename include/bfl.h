@@ -75,6 +75,11 @@ int bfl_ctx_destroy(bfl_ctx* ctx);
 int bfl_ctx_sync(bfl_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t bfl_ctx_launch_count(const bfl_ctx* ctx);
+/* Measurement: when enabled, every launch of the fused window kernel is bracketed by CUDA
+ * events on the context's stream.  bfl_ctx_window_time synchronises the stream, returns the
+ * summed duration (ms) and the number of launches since the last call, and resets both.     */
+int bfl_ctx_set_timing(bfl_ctx* ctx, int enable);
+int bfl_ctx_window_time(bfl_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* ---- plan: templates + per-grid-point constants, built on device --------------------
  * Replaces the model/prior/cross-term set-up loop of Bayes.bayes_factors_marg_poly_bgd
@@ -104,12 +109,15 @@ int bfl_window_lnB(bfl_ctx* ctx, bfl_plan* plan, int ihyp, const double* clc, co
  * the polynomial-only noise model first, as find.py:774-782 does.  For a batch of B light
  * curves on the same time base:
  *   clc, cle host [B][N] (cle NULL = zeros), sk host [B]
- *   out_lnO  host [B][N]   log odds for EVERY sample (callers drop the first/last W/2 when
- *                          ignoreedges, find.py:846-851)
- *   out_marg host [(nhyp+1)][B][N] or NULL: marginalised log Bayes factor of each hypothesis
+ *   [k0, k1)               samples to produce: (0, N) for every sample, (W/2, N - W/2) when the
+ *                          caller ignores the edges (find.py:846-851) -- the truncated-window
+ *                          samples are then never computed
+ *   out_lnO  host [B][k1-k0] log odds
+ *   out_marg host [(nhyp+1)][B][k1-k0] or NULL: marginalised log Bayes factor of each hypothesis
  *                          (index nhyp = polynomial-only), without the sumlogsigma constant  */
 int bfl_detector_odds(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double* clc, const double* cle,
-                      const double* sk, int32_t B, int64_t N, double* out_lnO, double* out_marg);
+                      const double* sk, int32_t B, int64_t N, int64_t k0, int64_t k1, double* out_lnO,
+                      double* out_marg);
 
 /* Same, device resident and asynchronous on the context's stream.  Supports time chunks:
  * the buffers hold samples [seg0, seg0+seglen) of series of true length N; log odds are
@@ -120,6 +128,12 @@ int bfl_detector_odds(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double*
 int bfl_detector_odds_dev(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double* d_clc,
                           const double* d_cle, int const_var, const double* d_sk, int32_t B, int64_t N,
                           int64_t seg0, int64_t seglen, int64_t k0, int64_t k1, double* d_lnO);
+
+/* Number of contiguous above-threshold regions (contiguous_regions, find.py:15-52) of each
+ * curve of a device-resident batch d_lnO[B][n] -> d_counts[B] (int64, overwritten).
+ * Asynchronous on the context's stream; feeds the multi-GPU detection-count reduction.      */
+int bfl_count_regions_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh,
+                          int64_t* d_counts);
 
 /* ---- OddsRatioDetector.thresholder (find.py:915-1019) on device ----------------------
  * contiguous regions of lnO > thresh, expanded by `expand` and merged; per region the
