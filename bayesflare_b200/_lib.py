@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbfl.so")
+LIB_PATH = os.environ.get("BFL_LIB") or os.path.join(HERE, "libbfl.so")
 
 MODEL_KINDS = {"flare": 0, "expdecay": 1, "impulse": 2, "step": 3, "transit": 4, "gaussian": 5, "table": 6}
 

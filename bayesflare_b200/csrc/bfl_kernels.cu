@@ -28,6 +28,7 @@
 #include "bfl_kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace bfl {
 
@@ -53,57 +54,61 @@ __device__ __forceinline__ double phi_half(double z) {
 #include "phi_table.inc"
 
 // phi(z) from the piecewise degree-6 table (tools/gen_phi_table.py; |error| < 2e-14), `tab` is the
-// shared-memory copy laid out [coefficient][interval].  Branch-free on [-12.06, 9.06]; beyond it
-// erfc(-z/sqrt2) = 2 to 1e-19 (z large) or the erfcx form is used (z very negative, rare).
-__device__ __forceinline__ double phi_half_tab(double z, const double* __restrict__ tab) {
+// shared-memory copy laid out [coefficient][interval].  Straight-line code: the interval index is
+// clamped, and because the last interval is stored as the exact quadratic z^2/2 + log 2 (erfc = 2
+// to 1e-19 there) clamping extrapolates correctly for any larger z.  Only z < -12.06 needs the
+// erfcx form (phi_half_far), which callers apply in a rarely-taken fix-up branch.
+// A second table block holds the full-range function z^2/2 in the same format, so both kinds of
+// hypothesis run the same instruction stream with a different table offset.
+#define BFL_PHI_STRIDE ((BFL_PHI_DEG + 1) * BFL_PHI_NI)
+#define BFL_PHI_ZFAR (-12.0625)
+__device__ __forceinline__ double phi_tab(double z, const double* __restrict__ tab) {
   const double s = fma(z, BFL_PHI_INVH, -(BFL_PHI_ZMIN) * BFL_PHI_INVH);
   int k = __double2int_rn(s);
   k = min(max(k, 0), BFL_PHI_NI - 1);
   const double x = s - (double)k;
-  double v = tab[6 * BFL_PHI_NI + k];
-  v = fma(v, x, tab[5 * BFL_PHI_NI + k]);
-  v = fma(v, x, tab[4 * BFL_PHI_NI + k]);
-  v = fma(v, x, tab[3 * BFL_PHI_NI + k]);
-  v = fma(v, x, tab[2 * BFL_PHI_NI + k]);
-  v = fma(v, x, tab[1 * BFL_PHI_NI + k]);
-  v = fma(v, x, tab[k]);
-  if (z > 9.0625) v = fma(0.5 * z, z, BFL_LN2);
-  else if (z < -12.0625) v = log(erfcx(-z * 0.70710678118654752440));
+  const double* c = tab + k;
+  double v = c[6 * BFL_PHI_NI];
+  v = fma(v, x, c[5 * BFL_PHI_NI]);
+  v = fma(v, x, c[4 * BFL_PHI_NI]);
+  v = fma(v, x, c[3 * BFL_PHI_NI]);
+  v = fma(v, x, c[2 * BFL_PHI_NI]);
+  v = fma(v, x, c[1 * BFL_PHI_NI]);
+  v = fma(v, x, c[0]);
   return v;
 }
+__device__ __noinline__ double phi_half_far(double z) {   // z < -12.06: log erfcx(-z/sqrt2)
+  return log(erfcx(-z * 0.70710678118654752440));
+}
 
-// e^d for d <= 0 (NaN propagates): magic-number range reduction, degree-11 polynomial on
-// |r| <= ln2/2 (relative error < 7e-15), exponent patched in with integer arithmetic.
-__device__ __forceinline__ double exp_nonpos(double d) {
+// e^d for d <= 0 (NaN propagates).  d = (64 e + j) ln2/64 + r with |r| <= ln2/128:
+// e^d = 2^e * 2^(j/64) * e^r; 2^(j/64) comes from a 64-entry shared-memory table (`t64`), e^r from a
+// degree-5 polynomial (relative error < 1e-16), 2^e is patched into the exponent field.
+// Total relative error < 2e-15 (single-constant range reduction), ample for a log-sum-exp.
+__device__ __forceinline__ double exp_nonpos(double d, const double* __restrict__ t64) {
   d = (d < -700.0) ? -700.0 : d;
   const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
-  const double t = fma(d, 1.4426950408889634074, MAGIC);
+  const double t = fma(d, 92.332482616893656877, MAGIC);          // 64 / ln 2
   const int n = __double2loint(t);
   const double nf = t - MAGIC;
-  double r = fma(nf, -6.93147180369123816490e-01, d);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = 2.50521083854417187751e-08;      // 1/11!
-  p = fma(p, r, 2.75573192239858906526e-07);  // 1/10!
-  p = fma(p, r, 2.75573192239858906526e-06);  // 1/9!
-  p = fma(p, r, 2.48015873015873015873e-05);  // 1/8!
-  p = fma(p, r, 1.98412698412698412698e-04);  // 1/7!
-  p = fma(p, r, 1.38888888888888888889e-03);  // 1/6!
-  p = fma(p, r, 8.33333333333333333333e-03);  // 1/5!
-  p = fma(p, r, 4.16666666666666666667e-02);  // 1/4!
-  p = fma(p, r, 1.66666666666666666667e-01);  // 1/3!
+  const double r = fma(nf, -1.0830424696249145e-02, d);           // ln 2 / 64
+  double p = 8.33333333333333333333e-03;                          // 1/5!
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  p *= t64[n & 63];
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
 }
 
 // online log-sum-exp, branch-free: m = running maximum (starts at LSE_EMPTY), s = sum exp(x_i - m)
 #define LSE_EMPTY (-1.0e300)
-__device__ __forceinline__ void lse_push(double& m, double& s, double x) {
+__device__ __forceinline__ void lse_push(double& m, double& s, double x, const double* __restrict__ t64) {
   const double d = x - m;
-  const double e = exp_nonpos(-fabs(d));
+  const double e = exp_nonpos(-fabs(d), t64);
   const bool up = d > 0.0;
-  s = up ? fma(s, e, 1.0) : (s + e);
+  s = fma(s, up ? e : 1.0, up ? 1.0 : e);
   m = up ? x : m;
 }
 
@@ -287,7 +292,8 @@ struct FastArgs {
   const double* sqrtu;    // [B]
   const double* halflogv; // [B]
   int64_t seglen, N, seg0, k0, k1;
-  int B, tiles_per_curve;
+  int B, tiles_per_curve;   // tiles_per_curve: warp tiles (32*KT samples) per light curve
+  int64_t total_wtiles;
   const double* hat;      // [G][WP]
   const double* Kg;       // [G]
   const double* lp;       // [G]
@@ -305,93 +311,124 @@ struct FastArgs {
 
 constexpr int FAST_TPB = 128;
 
-// z for KT consecutive samples against one template (register window, compile-time W)
+// z for KT consecutive samples against one template (register window, compile-time W).
+// Two partial sums per sample, pairs of taps alternate between them: the order is the same for
+// every KT, so results do not depend on the tiling.
 template <int WT, int KT>
 __device__ __forceinline__ void correlate_reg(const double* __restrict__ t, const double* win, double (&z)[KT]) {
-  constexpr int NPAIR = (WT + 1) / 2;
-  constexpr int NACC = 2;   // same summation order for every KT: results do not depend on the tiling
-  double acc[KT][NACC];
+  constexpr int NPAIR = WT / 2;     // WT is odd: NPAIR pairs + one last tap
+  double acc[KT][2];
 #pragma unroll
-  for (int j = 0; j < KT; j++)
-#pragma unroll
-    for (int a = 0; a < NACC; a++) acc[j][a] = 0.0;
+  for (int j = 0; j < KT; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
   const double2* t2 = reinterpret_cast<const double2*>(t);
 #pragma unroll
   for (int w2 = 0; w2 < NPAIR; w2++) {
     const double2 m = t2[w2];
 #pragma unroll
     for (int j = 0; j < KT; j++) {
-      acc[j][w2 % NACC] = fma(m.x, win[2 * w2 + j], acc[j][w2 % NACC]);
-      acc[j][w2 % NACC] = fma(m.y, win[2 * w2 + 1 + j], acc[j][w2 % NACC]);
+      acc[j][w2 & 1] = fma(m.x, win[2 * w2 + j], acc[j][w2 & 1]);
+      acc[j][w2 & 1] = fma(m.y, win[2 * w2 + 1 + j], acc[j][w2 & 1]);
     }
   }
+  const double ml = t[WT - 1];
 #pragma unroll
-  for (int j = 0; j < KT; j++) {
-    double s = acc[j][0];
-#pragma unroll
-    for (int a = 1; a < NACC; a++) s += acc[j][a];
-    z[j] = s;
-  }
+  for (int j = 0; j < KT; j++) z[j] = fma(ml, win[WT - 1 + j], acc[j][NPAIR & 1]) + acc[j][(NPAIR + 1) & 1];
 }
 
 // WT > 0: compile-time window length with the data window in registers;
 // WT == 0: run-time window length (any odd W <= MAXW), data window read from shared memory, KT = 1.
+#ifndef BFL_PIPE
+#define BFL_PIPE 0
+#endif
+#ifndef BFL_MINBLOCKS
+#define BFL_MINBLOCKS 2
+#endif
+// Persistent kernel: the grid is sized to the number of CTAs the chip can hold; each CTA stages
+// its template chunk and the function tables into shared memory ONCE, then its warps walk over
+// "warp tiles" (32*KT consecutive samples of one light curve) independently of each other --
+// each warp stages its own data window (+ halo) into a private shared-memory slice, so the tile
+// loop contains no block-level barrier.
 template <int WT, int KT, int MODE>
-__global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
+__global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const FastArgs a) {
   extern __shared__ double smem[];
   const int W = (WT > 0) ? WT : a.W;
   const int H = W / 2;
   const int WP = a.WP;
-  constexpr int TK = FAST_TPB * KT;
-  const int tid = threadIdx.x;
-  const int tile = blockIdx.x % a.tiles_per_curve;
-  const int b = blockIdx.x / a.tiles_per_curve;
+  constexpr int WPB = FAST_TPB / 32;             // warps per block
+  constexpr int TKW = 32 * KT;                   // samples per warp tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = blockIdx.y;
-  const int64_t kbase = a.k0 + (int64_t)tile * TK;
   const int gb = chunk * a.gchunk;
   const int ge = min(a.G, gb + a.gchunk);
-  const int ndata = TK + 2 * H + 2;
+  const int wstride = (TKW + 2 * H + 2) & ~1;    // doubles per warp slice
 
-  double* sdata = smem;                          // [ndata] (padded to even)
-  double* stmpl = smem + ((ndata + 1) & ~1);     // [gchunk][WP]
-  double* sK = stmpl + (size_t)a.gchunk * WP;    // [gchunk]  Kg + lp (+ lw)
-  double* sphi = sK + ((a.gchunk + 1) & ~1);     // [(DEG+1) * NI] phi(z) table
+  double* sdata = smem;                                  // [WPB][wstride]
+  double* stmpl = smem + WPB * wstride;                  // [gchunk + 1][WP] (last row: zeros)
+  double* sK = stmpl + (size_t)(a.gchunk + 1) * WP;      // [gchunk]  Kg + lp (+ lw)
+  double* sphi = sK + ((a.gchunk + 1) & ~1);             // [2][(DEG+1) * NI] phi(z) and z^2/2 tables
+  double* st64 = sphi + 2 * BFL_PHI_STRIDE;              // [64] 2^(j/64)
 
-  // ---- stage the light-curve tile + halo (coalesced), pre-scaled by sqrt(1/v) ----
+  // ---- once per CTA: templates of this chunk (16-byte copies) and the function tables ----
   {
-    const double su = a.sqrtu[b];
-    const double* d = a.data + (size_t)b * a.seglen;
-    const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
-    for (int i = tid; i < ndata; i += FAST_TPB) {
-      const int64_t s = kbase - H + i;
-      double v = 0.0;
-      if (s >= lo && s < hi) v = __ldg(d + (s - a.seg0)) * su;
-      sdata[i] = v;
-    }
-    // templates of this chunk: vectorised 16-byte copies (rows are WP = even doubles)
     const double2* src = reinterpret_cast<const double2*>(a.hat + (size_t)gb * WP);
     double2* dst = reinterpret_cast<double2*>(stmpl);
     const int n2 = (ge - gb) * WP / 2;
     for (int i = tid; i < n2; i += FAST_TPB) dst[i] = __ldg(src + i);
+    for (int i = tid; i < WP; i += FAST_TPB) stmpl[(size_t)(ge - gb) * WP + i] = 0.0;   // pipeline pad row
     for (int i = tid; i < ge - gb; i += FAST_TPB) {
       double k = a.Kg[gb + i] + a.lp[gb + i];
       if (MODE == 0) k += a.lw[gb + i];
       sK[i] = k;
     }
-    for (int i = tid; i < (BFL_PHI_DEG + 1) * BFL_PHI_NI; i += FAST_TPB) sphi[i] = BFL_PHI_TAB[i];
+    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+    for (int i = tid; i < BFL_PHI_STRIDE; i += FAST_TPB) {
+      sphi[i] = BFL_PHI_TAB[i];
+      // full-range hypotheses: z^2/2 in the same per-interval format (exact quadratic)
+      const int c = i / BFL_PHI_NI, kk = i - c * BFL_PHI_NI;
+      const double zk = BFL_PHI_ZMIN + kk * (1.0 / BFL_PHI_INVH), hh = 1.0 / BFL_PHI_INVH;
+      sphi[BFL_PHI_STRIDE + i] = (c == 0) ? 0.5 * zk * zk : (c == 1) ? zk * hh : (c == 2) ? 0.5 * hh * hh : 0.0;
+    }
   }
   __syncthreads();
 
+  // templates of this chunk, restricted to one hypothesis in FULL mode
+  int g0 = gb, g1 = ge;
+  if (MODE == 1) { g0 = max(gb, a.hyp_begin[a.ihyp]); g1 = min(ge, a.hyp_begin[a.ihyp + 1]); }
+  if (g0 >= g1) return;
+  int h0 = 0;
+  while (a.hyp_begin[h0 + 1] <= g0) h0++;
+  const int64_t nk = a.k1 - a.k0;
+  double* swin = sdata + warp * wstride;
+
+  for (int64_t wt = (int64_t)blockIdx.x * WPB + warp; wt < a.total_wtiles; wt += (int64_t)gridDim.x * WPB) {
+  const int tile = (int)(wt % a.tiles_per_curve);
+  const int b = (int)(wt / a.tiles_per_curve);
+  const int64_t kbase = a.k0 + (int64_t)tile * TKW;
+
+  // ---- stage this warp's light-curve slice + halo (coalesced), pre-scaled by sqrt(1/v) ----
+  {
+    const double su = a.sqrtu[b];
+    const double* d = a.data + (size_t)b * a.seglen;
+    const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
+    __syncwarp();
+    for (int i = lane; i < TKW + 2 * H; i += 32) {
+      const int64_t sidx = kbase - H + i;
+      double v = 0.0;
+      if (sidx >= lo && sidx < hi) v = __ldg(d + (sidx - a.seg0)) * su;
+      swin[i] = v;
+    }
+    __syncwarp();
+  }
+
   // ---- the thread's data window ----
-  double win[(WT > 0) ? (WT + KT) : 1];
+  double win[(WT > 0) ? (WT + KT - 1) : 1];
   if constexpr (WT > 0) {
 #pragma unroll
-    for (int e = 0; e < WT + KT; e++) win[e] = (e < WT + KT - 1) ? sdata[tid * KT + e] : 0.0;
+    for (int e = 0; e < WT + KT - 1; e++) win[e] = swin[lane * KT + e];
   }
 
   const double hlv = a.halflogv[b];
-  const int64_t nk = a.k1 - a.k0;
-  const int64_t kfirst = kbase + (int64_t)tid * KT;
+  const int64_t kfirst = kbase + (int64_t)lane * KT;
 
   bool valid[KT];
 #pragma unroll
@@ -400,67 +437,113 @@ __global__ void __launch_bounds__(FAST_TPB) k_window_fast(const FastArgs a) {
     valid[j] = (k < a.k1) && (k >= H) && (k < a.N - H);   // interior samples only
   }
 
-  const int h_lo = (MODE == 0) ? 0 : max(a.ihyp, 0);
-  const int h_hi = (MODE == 0) ? a.nhyp : a.ihyp + 1;
-  for (int h = h_lo; h < h_hi; h++) {
-    const int lo = max(gb, a.hyp_begin[h]), hi = min(ge, a.hyp_begin[h + 1]);
-    if (lo >= hi) continue;
-    const bool half = a.hyp_half[h] != 0;
-    const double hc = (half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
-    double mx[KT], sm[KT];
-#pragma unroll
-    for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
+  auto correlate = [&](int gl, double (&z)[KT]) {
+    const double* t = stmpl + (size_t)gl * WP;
+    if constexpr (WT > 0) {
+      correlate_reg<WT, KT>(t, win, z);
+    } else {
+      double a0 = 0.0, a1 = 0.0;
+      const double* dd = swin + lane;
+      int w = 0;
+      for (; w + 1 < W; w += 2) { a0 = fma(t[w], dd[w], a0); a1 = fma(t[w + 1], dd[w + 1], a1); }
+      if (w < W) a0 = fma(t[w], dd[w], a0);
+      z[0] = a0 + a1;
+    }
+  };
 
-    for (int g = lo; g < hi; g++) {
-      const double* t = stmpl + (size_t)(g - gb) * WP;
-      double z[KT];
-      if constexpr (WT > 0) {
-        correlate_reg<WT, KT>(t, win, z);
-      } else {
-        double a0 = 0.0, a1 = 0.0;
-        const double* dd = sdata + tid;
-        int w = 0;
-        for (; w + 1 < W; w += 2) { a0 = fma(t[w], dd[w], a0); a1 = fma(t[w + 1], dd[w + 1], a1); }
-        if (w < W) a0 = fma(t[w], dd[w], a0);
-        z[0] = a0 + a1;
-      }
-      const double kg = sK[g - gb];
+  int h = h0;
+  double mx[KT], sm[KT];
+#pragma unroll
+  for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
+
+  auto flush = [&](int hh) {
+    if (MODE == 0) {
+      const double hc = (a.hyp_half[hh] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
+      double2* p = a.part + ((size_t)(hh * a.NC + chunk) * a.B + b) * nk;
 #pragma unroll
       for (int j = 0; j < KT; j++) {
-        const double val = kg + (half ? phi_half_tab(z[j], sphi) : 0.5 * z[j] * z[j]);
-        if (MODE == 0) {
-          lse_push(mx[j], sm[j], val);
-        } else if (valid[j]) {
+        if (valid[j]) p[kfirst + j - a.k0] = make_double2(mx[j] + hc, sm[j]);
+        mx[j] = LSE_EMPTY; sm[j] = 0.0;
+      }
+    }
+  };
+
+  // software pipeline: the correlation for template g+1 is issued in the same straight-line block
+  // as the (latency-bound) epilogue of template g; row (ge - gb) of stmpl is a zero pad row.
+  double zc[KT];
+#if BFL_PIPE
+  correlate(g0 - gb, zc);
+#endif
+  for (int g = g0; g < g1; g++) {
+#if BFL_PIPE
+    double zn[KT];
+    correlate(g + 1 - gb, zn);
+#elif defined(BFL_EXP_EPI_ONLY)
+#pragma unroll
+    for (int j = 0; j < KT; j++) zc[j] = (BFL_EPI_UNIFORM ? 0.0 : win[j] * 0.9 + win[j + 1] * 0.3) + 0.05 * (g - gb) - 2.0 + 1e-30 * win[j];
+#else
+    correlate(g - gb, zc);
+#endif
+    while (g >= a.hyp_begin[h + 1]) { flush(h); h++; }
+    const bool half = a.hyp_half[h] != 0;
+    const double* tab = sphi + (half ? 0 : BFL_PHI_STRIDE);
+    const double kg = sK[g - gb];
+    double val[KT];
+    bool far_ = false;
+#if defined(BFL_EXP_CORR_ONLY)
+#pragma unroll
+    for (int j = 0; j < KT; j++) { mx[j] += zc[j]; }
+    continue;
+#endif
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+      val[j] = kg + phi_tab(zc[j], tab);
+      far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
+    }
+    if (half && far_) {   // rare: a > 12 sigma negative amplitude
+#pragma unroll
+      for (int j = 0; j < KT; j++)
+        if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < KT; j++) lse_push(mx[j], sm[j], val[j], st64);
+    } else {
+      const double hc = (half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
+#pragma unroll
+      for (int j = 0; j < KT; j++) {
+        if (valid[j]) {
           const int64_t ki = kfirst + j - a.k0;
-          a.out_full[(size_t)a.gorig[g] * nk + ki] = (val + hc) + (a.bgabs[(size_t)b * nk + ki] + a.sls);
+          a.out_full[(size_t)a.gorig[g] * nk + ki] = (val[j] + hc) + (a.bgabs[(size_t)b * nk + ki] + a.sls);
         }
       }
     }
-    if (MODE == 0) {
-      double2* p = a.part + ((size_t)(h * a.NC + chunk) * a.B + b) * nk;
+#if BFL_PIPE
 #pragma unroll
-      for (int j = 0; j < KT; j++)
-        if (valid[j]) p[kfirst + j - a.k0] = make_double2(mx[j] + hc, sm[j]);
-    }
+    for (int j = 0; j < KT; j++) zc[j] = zn[j];
+#endif
   }
+  flush(h);
+  }   // warp-tile loop
 }
 
 size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int WP = W + 1;
-  const int ndata = FAST_TPB * KT + 2 * (W / 2) + 2;
-  return sizeof(double) * (size_t)(((ndata + 1) & ~1) + (size_t)gchunk * WP + ((gchunk + 1) & ~1) +
-                                   (BFL_PHI_DEG + 1) * BFL_PHI_NI);
+  const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
+  return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(gchunk + 1) * WP + ((gchunk + 1) & ~1) +
+                                   2 * BFL_PHI_STRIDE + 64);
 }
 
 // choose samples-per-thread and the template chunk so that the grid covers the chip
 int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out) {
   const int64_t want = 2LL * sm_count;   // at least two CTAs per SM when the problem allows
   int KT = 4;
+  if (const char* e = getenv("BFL_KT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) KT = v; }
   if (W != 55) KT = 1;
   else {
     while (KT > 1 && (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT) < want) KT >>= 1;
   }
-  const int64_t tiles = (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT);
+  const int64_t tiles = (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT);   // CTA-sized groups of warp tiles
   const int WP = W + 1;
   int gmax = (int)((96 * 1024) / (sizeof(double) * (WP + 1)));   // <= 96 KB of templates per CTA
   if (gmax < 1) gmax = 1;
@@ -485,7 +568,8 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
   a.seglen = sv.seglen; a.N = sv.N; a.seg0 = sv.seg0; a.k0 = sv.k0; a.k1 = sv.k1;
   a.B = sv.B;
   const int64_t nk = sv.k1 - sv.k0;
-  a.tiles_per_curve = (int)((nk + FAST_TPB * KT - 1) / (FAST_TPB * KT));
+  a.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
+  a.total_wtiles = (int64_t)a.tiles_per_curve * sv.B;
   a.hat = pv.hat; a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.gorig = pv.gorig;
   a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.gchunk = sc.gchunk; a.NC = sc.NC; a.nhyp = pv.nhyp;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
@@ -497,13 +581,28 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
 template <int MODE>
 static cudaError_t launch_fast_impl(FastArgs& a, int KT, cudaStream_t s, LaunchStats* st) {
   const size_t smem = fast_smem_bytes(a.W, a.gchunk, KT);
-  dim3 grid((unsigned)(a.tiles_per_curve * a.B), (unsigned)a.NC);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   cudaError_t e = cudaSuccess;
+  // persistent grid: as many CTAs as the device holds at once (or fewer if there is less work)
 #define BFL_LAUNCH(WT_, KT_)                                                                              \
   do {                                                                                                    \
     e = cudaFuncSetAttribute(k_window_fast<WT_, KT_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                              (int)smem);                                                                  \
     if (e != cudaSuccess) return e;                                                                       \
+    int occ = 1;                                                                                          \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_window_fast<WT_, KT_, MODE>, FAST_TPB, smem); \
+    if (e != cudaSuccess) return e;                                                                       \
+    if (occ < 1) occ = 1;                                                                                 \
+    int64_t gx = ((int64_t)sms * occ + a.NC - 1) / a.NC;                                                  \
+    const int64_t need = (a.total_wtiles + FAST_TPB / 32 - 1) / (FAST_TPB / 32);                          \
+    if (gx > need) gx = need;                                                                             \
+    if (gx < 1) gx = 1;                                                                                   \
+    dim3 grid((unsigned)gx, (unsigned)a.NC);                                                              \
     k_window_fast<WT_, KT_, MODE><<<grid, FAST_TPB, smem, s>>>(a);                                        \
   } while (0)
   if (a.W == 55 && KT == 4) BFL_LAUNCH(55, 4);
@@ -753,6 +852,8 @@ __global__ void k_window_general(const GenArgs a) {
   double* stm = sbb + NPAIR * WP;           // [gchunk][WP]
   double* swu = stm + (size_t)a.gchunk * WP;// [W][TPB]  noise-variance window, transposed
   double* swd = swu + (size_t)W * TPB;      // [W][TPB]  d/v window, transposed
+  double* st64 = swd + (size_t)W * TPB;     // [64] 2^(j/64) for the log-sum-exp
+  for (int i = tid; i < 64; i += TPB) st64[i] = exp2((double)i * (1.0 / 64.0));
 
   for (int i = tid; i < P * WP; i += TPB) sbg[i] = a.bg[i];
   for (int i = tid; i < NPAIR * WP; i += TPB) sbb[i] = a.bb[i];
@@ -833,7 +934,7 @@ __global__ void k_window_general(const GenArgs a) {
       for (int i = 0; i < n; i++) dm = fma(swd[(w0 + i) * TPB + tid], m[i], dm);
       const double lnB = signal_logL<P>(el, mdbg, mm, dm, half);
       if (MODE == 0) {
-        lse_push(mx, sm, (lnB - lnBbg) + (a.lp[g] + a.lw[g]));
+        lse_push(mx, sm, (lnB - lnBbg) + (a.lp[g] + a.lw[g]), st64);
       } else {
         a.out_full[(size_t)a.gorig[g] * nk + (k - a.k0)] = (lnB + a.sls) + a.lp[g];
       }
@@ -844,7 +945,7 @@ __global__ void k_window_general(const GenArgs a) {
 
 static size_t general_smem(int P, int W, int gchunk, int tpb) {
   const int WP = W + 1;
-  return sizeof(double) * ((size_t)(P + P * (P + 1) / 2 + gchunk) * WP + (size_t)2 * W * tpb);
+  return sizeof(double) * ((size_t)(P + P * (P + 1) / 2 + gchunk) * WP + (size_t)2 * W * tpb + 64);
 }
 
 template <int MODE>
