@@ -1,0 +1,93 @@
+"""CPU tests of the N>1 host logic: sharding helpers and result aggregation with a world_size-2
+gloo process group (the same code runs over NCCL on the GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from bayesflare_b200 import parallel
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = parallel.shard_range(n, world, r)
+                assert 0 <= lo <= hi <= n
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+            sizes = [parallel.shard_range(n, world, r)[1] - parallel.shard_range(n, world, r)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("ignoreedges", [True, False])
+def test_time_chunks_cover_series_with_halos(ignoreedges):
+    N, W = 130000, 55
+    chunks = parallel.time_chunks(N, 8, W, ignoreedges)
+    h = W // 2
+    first, last = (h, N - h) if ignoreedges else (0, N)
+    assert chunks[0][0] == first and chunks[-1][1] == last
+    for (k0, k1, s0, s1), nxt in zip(chunks, chunks[1:] + [None]):
+        assert s0 == max(0, k0 - h) and s1 == min(N, k1 + h)      # every window is inside its segment
+        if nxt:
+            assert nxt[0] == k1
+    assert parallel.time_chunks(100, 200, 55)[-1][1] == 100 - 27      # more chunks than samples: empties dropped
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # each rank "detects" a different number of flares in its shard of 10 curves
+        lo, hi = parallel.shard_range(10, world, rank)
+        rec = np.array([[c, 100 + c, 105 + c, 102 + c, 17.0 + c] for c in range(lo, hi) if c % 3 != 1], dtype=float)
+        rec = rec.reshape(-1, 5)
+        allrec = parallel.gather_detections(rec)
+        hist = np.zeros(50, dtype=np.int64)
+        hist[rank::7] = rank + 1
+        tot = parallel.allreduce_counts(hist)
+        empty = parallel.gather_detections(np.zeros((0, 5)))
+        q.put((rank, allrec, tot, empty.shape))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_and_reduce_world2_gloo():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = np.array([[c, 100 + c, 105 + c, 102 + c, 17.0 + c] for c in range(10) if c % 3 != 1], dtype=float)
+    hist = np.zeros(50, dtype=np.int64)
+    hist[0::7] += 1
+    hist[1::7] += 2
+    for rank, allrec, tot, eshape in res:
+        np.testing.assert_array_equal(allrec, expect)      # identical on every rank, rank order preserved
+        np.testing.assert_array_equal(tot, hist)
+        assert eshape == (0, 5)
+
+
+def test_single_process_is_a_no_op():
+    rec = np.arange(10.0).reshape(2, 5)
+    np.testing.assert_array_equal(parallel.gather_detections(rec), rec)
+    np.testing.assert_array_equal(parallel.allreduce_counts([1, 2, 3]), [1, 2, 3])
