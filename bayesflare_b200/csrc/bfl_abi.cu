@@ -333,6 +333,7 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   sc.gchunk = pick_gchunk(std::max(pv.G, 1), pv.W, (int64_t)sv.B * nk, c->sm_count, &KT);
   sc.KT = KT;
   sc.NC = (std::max(pv.G, 1) + sc.gchunk - 1) / sc.gchunk;
+  sc.sub = (sv.const_var && fast_uses_ws(pv.W, KT, sc.gchunk)) ? 2 : 1;
   int rc;
   void* ptr;
   if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;
@@ -345,7 +346,7 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   }
   sc.part = nullptr;
   if (need_part) {
-    if ((rc = c->get("part", sizeof(double2) * (size_t)std::max(pv.nhyp, 1) * sc.NC * sv.B * nk, &ptr))) return rc;
+    if ((rc = c->get("part", sizeof(double2) * (size_t)std::max(pv.nhyp, 1) * sc.NC * sc.sub * sv.B * nk, &ptr))) return rc;
     sc.part = (double2*)ptr;
   }
   sc.bgabs = nullptr;

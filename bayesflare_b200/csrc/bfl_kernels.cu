@@ -527,6 +527,241 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   }   // warp-tile loop
 }
 
+// ======================================================================================
+// FAST path, warp-specialised variant (W = 55, large batches)
+// ======================================================================================
+// One persistent CTA per SM: 4 PRODUCER warps (one per SM sub-partition) hold the register
+// data window and do nothing but the correlation z = m_hat . d for template after template;
+// 8 CONSUMER warps (two per producer) take z through a shared-memory ring and run the
+// latency/LSU-bound part: phi(z) table look-up, log-sum-exp.  Producers keep the FP64 pipe fed
+// while consumers wait on shared-memory latency, which an in-order warp doing both cannot.
+// Ring slots are handed over with mbarriers (full / empty, one arrival each).
+constexpr int WS_D = 8;            // ring depth in templates
+constexpr int WS_NP = 4;           // producer warps
+constexpr int WS_NC = 2;           // consumers per producer
+constexpr int WS_THREADS = 32 * WS_NP * (1 + WS_NC);
+constexpr int WS_W = 55, WS_KT = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_window_ws(const FastArgs a) {
+  extern __shared__ double smem[];
+  constexpr int W = WS_W, H = W / 2, KT = WS_KT, TKW = 32 * KT;
+  const int WP = a.WP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.y;
+  const int gb = chunk * a.gchunk;
+  const int ge = min(a.G, gb + a.gchunk);
+  constexpr int wstride = (TKW + 2 * H + 2) & ~1;
+
+  double* swinall = smem;                                    // [WS_NP][wstride]
+  double* zring = swinall + WS_NP * wstride;                 // [WS_NP][WS_D][KT][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zring + WS_NP * WS_D * KT * 32);   // full[NP][D], empty[NP][D]
+  double* stmpl = reinterpret_cast<double*>(bars + 2 * WS_NP * WS_D);             // [gchunk][WP]
+  double* sK = stmpl + (size_t)a.gchunk * WP;                // [gchunk]
+  double* sphi = sK + ((a.gchunk + 1) & ~1);                 // [2][(DEG+1)*NI]
+  double* st64 = sphi + 2 * BFL_PHI_STRIDE;                  // [64]
+
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.hat + (size_t)gb * WP);
+    double2* dst = reinterpret_cast<double2*>(stmpl);
+    const int n2 = (ge - gb) * WP / 2;
+    for (int i = tid; i < n2; i += WS_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < ge - gb; i += WS_THREADS) {
+      double k = a.Kg[gb + i] + a.lp[gb + i];
+      if (MODE == 0) k += a.lw[gb + i];
+      sK[i] = k;
+    }
+    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+    for (int i = tid; i < BFL_PHI_STRIDE; i += WS_THREADS) {
+      sphi[i] = BFL_PHI_TAB[i];
+      const int c = i / BFL_PHI_NI, kk = i - c * BFL_PHI_NI;
+      const double zk = BFL_PHI_ZMIN + kk * (1.0 / BFL_PHI_INVH), hh = 1.0 / BFL_PHI_INVH;
+      sphi[BFL_PHI_STRIDE + i] = (c == 0) ? 0.5 * zk * zk : (c == 1) ? zk * hh : (c == 2) ? 0.5 * hh * hh : 0.0;
+    }
+    if (tid < WS_NP * WS_D) {
+      mbar_init(bars + tid, 1);                        // full: the producer's lane 0
+      mbar_init(bars + WS_NP * WS_D + tid, 1);         // empty: lane 0 of the consumer that owns the template
+    }
+  }
+  __syncthreads();
+
+  int g0 = gb, g1 = ge;
+  if (MODE == 1) { g0 = max(gb, a.hyp_begin[a.ihyp]); g1 = min(ge, a.hyp_begin[a.ihyp + 1]); }
+  if (g0 >= g1) return;
+  const int64_t nk = a.k1 - a.k0;
+  const bool producer = warp < WS_NP;
+  const int p = producer ? warp : (warp - WS_NP) % WS_NP;     // ring id == SM sub-partition
+  const int c = producer ? 0 : (warp - WS_NP) / WS_NP;        // consumer index within the ring
+  uint64_t* full = bars + p * WS_D;
+  uint64_t* empty = bars + WS_NP * WS_D + p * WS_D;
+  double* ring = zring + (size_t)p * WS_D * KT * 32;
+  uint32_t step = 0;                                           // templates handed over so far
+
+  for (int64_t wt = (int64_t)blockIdx.x * WS_NP + p; wt < a.total_wtiles; wt += (int64_t)gridDim.x * WS_NP) {
+    const int tile = (int)(wt % a.tiles_per_curve);
+    const int b = (int)(wt / a.tiles_per_curve);
+    const int64_t kbase = a.k0 + (int64_t)tile * TKW;
+
+    if (producer) {
+      // ---- stage this warp's slice + halo, then keep the window in registers ----
+      double* swin = swinall + warp * wstride;
+      {
+        const double su = a.sqrtu[b];
+        const double* d = a.data + (size_t)b * a.seglen;
+        const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
+        __syncwarp();
+        for (int i = lane; i < TKW + 2 * H; i += 32) {
+          const int64_t sidx = kbase - H + i;
+          double v = 0.0;
+          if (sidx >= lo && sidx < hi) v = __ldg(d + (sidx - a.seg0)) * su;
+          swin[i] = v;
+        }
+        __syncwarp();
+      }
+      double win[W + KT - 1];
+#pragma unroll
+      for (int e = 0; e < W + KT - 1; e++) win[e] = swin[lane * KT + e];
+      for (int g = g0; g < g1; g++, step++) {
+        double z[KT];
+#ifdef BFL_WS_NOCORR
+#pragma unroll
+        for (int j = 0; j < KT; j++) z[j] = win[j] * 0.9 + win[j + 1] * 0.3 + 0.01 * (g - gb);
+#else
+        correlate_reg<W, KT>(stmpl + (size_t)(g - gb) * WP, win, z);
+#endif
+        const int slot = step % WS_D;
+        mbar_wait(empty + slot, ((step / WS_D) & 1) ^ 1);
+        double* dst = ring + (size_t)slot * KT * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < KT; j++) dst[j * 32] = z[j];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + slot);
+      }
+    } else {
+      // ---- consumer c: every KT samples of the lane, templates of parity c (within the chunk).
+      // Each consumer keeps its own partial log-sum-exp; the two are merged by k_combine
+      // (sub-chunk index = consumer index).
+      const double hlv = a.halflogv[b];
+      const int64_t kfirst = kbase + (int64_t)lane * KT;
+      bool valid[KT];
+#pragma unroll
+      for (int j = 0; j < KT; j++) {
+        const int64_t k = kfirst + j;
+        valid[j] = (k < a.k1) && (k >= H) && (k < a.N - H);
+      }
+      int h = 0;
+      while (a.hyp_begin[h + 1] <= g0) h++;
+      double mx[KT], sm[KT];
+#pragma unroll
+      for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
+      auto flush = [&](int hh) {
+        if (MODE == 0) {
+          const double hc = (a.hyp_half[hh] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
+          double2* pp = a.part + ((size_t)(hh * a.NC * WS_NC + chunk * WS_NC + c) * a.B + b) * nk;
+#pragma unroll
+          for (int j = 0; j < KT; j++) {
+            if (valid[j]) pp[kfirst + j - a.k0] = make_double2(mx[j] + hc, sm[j]);
+            mx[j] = LSE_EMPTY; sm[j] = 0.0;
+          }
+        }
+      };
+      for (int g = g0; g < g1; g++, step++) {
+        while (g >= a.hyp_begin[h + 1]) { flush(h); h++; }
+        const int slot = step % WS_D;
+        if (((g - g0) & 1) != c) continue;                      // the other consumer's template
+        const bool half = a.hyp_half[h] != 0;
+        const double* tab = sphi + (half ? 0 : BFL_PHI_STRIDE);
+        const double kg = sK[g - gb];
+        mbar_wait(full + slot, (step / WS_D) & 1);
+        const double* src = ring + (size_t)slot * KT * 32 + lane;
+        double zc[KT];
+#pragma unroll
+        for (int j = 0; j < KT; j++) zc[j] = src[j * 32];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+#ifdef BFL_WS_NOEPI
+#pragma unroll
+        for (int j = 0; j < KT; j++) mx[j] += zc[j];
+        continue;
+#endif
+        double val[KT];
+        bool far_ = false;
+#pragma unroll
+        for (int j = 0; j < KT; j++) {
+          val[j] = kg + phi_tab(zc[j], tab);
+          far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
+        }
+        if (half && far_) {
+#pragma unroll
+          for (int j = 0; j < KT; j++)
+            if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < KT; j++) lse_push(mx[j], sm[j], val[j], st64);
+        } else {
+          const double hc = (half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
+#pragma unroll
+          for (int j = 0; j < KT; j++) {
+            if (valid[j]) {
+              const int64_t ki = kfirst + j - a.k0;
+              a.out_full[(size_t)a.gorig[g] * nk + ki] = (val[j] + hc) + (a.bgabs[(size_t)b * nk + ki] + a.sls);
+            }
+          }
+        }
+      }
+      flush(h);
+    }
+  }
+}
+
+static size_t ws_smem_bytes(int gchunk) {
+  const int WP = WS_W + 1;
+  const int wstride = (32 * WS_KT + 2 * (WS_W / 2) + 2) & ~1;
+  return sizeof(double) * (size_t)(WS_NP * wstride + WS_NP * WS_D * WS_KT * 32 + 2 * WS_NP * WS_D +
+                                   (size_t)gchunk * WP + ((gchunk + 1) & ~1) + 2 * BFL_PHI_STRIDE + 64);
+}
+
+template <int MODE>
+static cudaError_t launch_ws_impl(FastArgs& a, cudaStream_t s, LaunchStats* st) {
+  const size_t smem = ws_smem_bytes(a.gchunk);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  cudaError_t e = cudaFuncSetAttribute(k_window_ws<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int64_t gx = (sms + a.NC - 1) / a.NC;
+  const int64_t need = (a.total_wtiles + WS_NP - 1) / WS_NP;
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)a.NC);
+  k_window_ws<MODE><<<grid, WS_THREADS, smem, s>>>(a);
+  st->launches++;
+  return cudaGetLastError();
+}
+
 size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int WP = W + 1;
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
@@ -538,7 +773,7 @@ size_t fast_smem_bytes(int W, int gchunk, int KT) {
 int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out) {
   const int64_t want = 2LL * sm_count;   // at least two CTAs per SM when the problem allows
   int KT = 4;
-  if (const char* e = getenv("BFL_KT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) KT = v; }
+  if (const char* e = getenv("BFL_KT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) KT = v; }
   if (W != 55) KT = 1;
   else {
     while (KT > 1 && (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT) < want) KT >>= 1;
@@ -605,13 +840,27 @@ static cudaError_t launch_fast_impl(FastArgs& a, int KT, cudaStream_t s, LaunchS
     dim3 grid((unsigned)gx, (unsigned)a.NC);                                                              \
     k_window_fast<WT_, KT_, MODE><<<grid, FAST_TPB, smem, s>>>(a);                                        \
   } while (0)
-  if (a.W == 55 && KT == 4) BFL_LAUNCH(55, 4);
+  if (a.W == 55 && KT == 8) BFL_LAUNCH(55, 8);
+  else if (a.W == 55 && KT == 4) BFL_LAUNCH(55, 4);
   else if (a.W == 55 && KT == 2) BFL_LAUNCH(55, 2);
   else if (a.W == 55 && KT == 1) BFL_LAUNCH(55, 1);
   else BFL_LAUNCH(0, 1);
 #undef BFL_LAUNCH
   st->launches++;
   return cudaGetLastError();
+}
+
+// the warp-specialised kernel targets the large-batch case (W = 55, KT = 4, enough tiles for every SM)
+bool fast_uses_ws(int W, int KT, int gchunk);
+static bool use_ws(const FastArgs& a, int KT) { return fast_uses_ws(a.W, KT, a.gchunk); }
+bool fast_uses_ws(int W, int KT, int gchunk) {
+  // Opt-in (BFL_WS=1).  Measured on B200 (round 1): 3.50 ms against 3.13 ms for the single-role
+  // persistent kernel on the 1,024-curve batch -- producers and consumers end up waiting on each
+  // other (30 % of stall samples sit in the mbarrier wait), so it is kept as an experiment only.
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("BFL_WS"); enabled = (e && atoi(e)) ? 1 : 0; }
+  if (!enabled) return false;
+  return W == WS_W && KT == WS_KT && ws_smem_bytes(gchunk) <= 200 * 1024;
 }
 
 static int kt_for(const PlanView& pv, const SeriesView& sv, const Scratch& sc) {
@@ -625,6 +874,7 @@ cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scr
   FastArgs a;
   const int KT = kt_for(pv, sv, sc);
   fill_fast_args(a, pv, sv, sc, KT);
+  if (use_ws(a, KT)) return launch_ws_impl<0>(a, s, st);
   return launch_fast_impl<0>(a, KT, s, st);
 }
 
@@ -635,6 +885,7 @@ cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesVi
   const int KT = kt_for(pv, sv, sc);
   fill_fast_args(a, pv, sv, sc, KT);
   a.out_full = d_out; a.sls = sumlogsigma; a.ihyp = ihyp;
+  if (use_ws(a, KT)) return launch_ws_impl<1>(a, s, st);
   return launch_fast_impl<1>(a, KT, s, st);
 }
 
@@ -826,7 +1077,7 @@ struct GenArgs {
   int B, tiles_per_curve, edges_only, tpb;
   const double* raw; const double* lp; const double* lw; const int* gorig;
   const double* bg; const double* bb;
-  int G, W, WP, gchunk, NC, nhyp;
+  int G, W, WP, gchunk, NC, nhyp, sub;
   int hyp_begin[MAXH + 1];
   int hyp_half[MAXH];
   double2* part;
@@ -939,7 +1190,10 @@ __global__ void k_window_general(const GenArgs a) {
         a.out_full[(size_t)a.gorig[g] * nk + (k - a.k0)] = (lnB + a.sls) + a.lp[g];
       }
     }
-    if (MODE == 0) a.part[(size_t)(h * a.NC + chunk) * a.B * nk + ki] = make_double2(mx, sm);
+    if (MODE == 0) {
+      a.part[(size_t)((h * a.NC + chunk) * a.sub) * a.B * nk + ki] = make_double2(mx, sm);
+      for (int u = 1; u < a.sub; u++) a.part[(size_t)((h * a.NC + chunk) * a.sub + u) * a.B * nk + ki] = make_double2(LSE_EMPTY, 0.0);
+    }
   }
 }
 
@@ -978,7 +1232,7 @@ static void fill_gen_args(GenArgs& a, const PlanView& pv, const SeriesView& sv, 
   a.tiles_per_curve = (int)((cnt + a.tpb - 1) / a.tpb);
   if (a.tiles_per_curve < 1) a.tiles_per_curve = 1;
   a.raw = pv.raw; a.lp = pv.lp; a.lw = pv.lw; a.gorig = pv.gorig; a.bg = pv.bg; a.bb = pv.bb;
-  a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.gchunk = sc.gchunk; a.NC = sc.NC; a.nhyp = pv.nhyp;
+  a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.gchunk = sc.gchunk; a.NC = sc.NC; a.nhyp = pv.nhyp; a.sub = sc.sub;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   for (int h = 0; h < pv.nhyp; h++) a.hyp_half[h] = pv.hyp_half[h];
   a.part = sc.part; a.bgabs = sc.bgabs; a.out_full = nullptr; a.sls = 0.0; a.ihyp = 0;
@@ -1007,7 +1261,7 @@ struct CombArgs {
   const double2* part;
   const double* bgabs;
   int64_t BK;          // B * nk
-  int nhyp, NC, gchunk, G, noisepoly;
+  int nhyp, NC, gchunk, G, noisepoly, sub;   // sub: partials per template chunk (2 with the warp-specialised kernel)
   int hyp_begin[MAXH + 1];
   double* lnO;
   double* marg;        // [(nhyp+1)][BK] or nullptr
@@ -1021,14 +1275,14 @@ __global__ void k_combine(const CombArgs a) {
     double M = neg_inf();
     const int c0 = a.hyp_begin[h] / a.gchunk;
     const int c1 = (a.hyp_begin[h + 1] > a.hyp_begin[h]) ? (a.hyp_begin[h + 1] - 1) / a.gchunk : c0 - 1;
-    for (int c = c0; c <= c1; c++) {
-      const double2 p = a.part[(size_t)(h * a.NC + c) * a.BK + i];
+    for (int c = c0 * a.sub; c < (c1 + 1) * a.sub; c++) {
+      const double2 p = a.part[(size_t)(h * a.NC * a.sub + c) * a.BK + i];
       if (p.y > 0.0 || isnan(p.y)) M = fmax(M, p.x);
     }
     double S = 0.0;
     bool nan_ = false;
-    for (int c = c0; c <= c1; c++) {
-      const double2 p = a.part[(size_t)(h * a.NC + c) * a.BK + i];
+    for (int c = c0 * a.sub; c < (c1 + 1) * a.sub; c++) {
+      const double2 p = a.part[(size_t)(h * a.NC * a.sub + c) * a.BK + i];
       if (isnan(p.x) || isnan(p.y)) nan_ = true;
       if (p.y > 0.0) S += p.y * exp(p.x - M);
     }
@@ -1058,7 +1312,7 @@ cudaError_t launch_combine(const PlanView& pv, const SeriesView& sv, const Scrat
   CombArgs a;
   a.part = sc.part; a.bgabs = sc.bgabs;
   a.BK = (int64_t)sv.B * (sv.k1 - sv.k0);
-  a.nhyp = pv.nhyp; a.NC = sc.NC; a.gchunk = sc.gchunk; a.G = pv.G; a.noisepoly = noisepoly;
+  a.nhyp = pv.nhyp; a.NC = sc.NC; a.gchunk = sc.gchunk; a.G = pv.G; a.noisepoly = noisepoly; a.sub = sc.sub;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   a.lnO = d_lnO; a.marg = d_marg;
   k_combine<<<(unsigned)((a.BK + 255) / 256), 256, 0, s>>>(a);

@@ -56,6 +56,7 @@ struct Scratch {
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
+  int sub;         // partials per template chunk: 2 when the warp-specialised kernel runs, else 1
 };
 
 struct LaunchStats { int64_t launches = 0; };
@@ -102,6 +103,7 @@ cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double t
 cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
 
 size_t fast_smem_bytes(int W, int gchunk, int KT);
+bool fast_uses_ws(int W, int KT, int gchunk);
 int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out);
 
 }  // namespace bfl
