@@ -39,6 +39,8 @@ struct bfl_ctx {
   bool own_stream = false;
   LaunchStats stats;
   bool timing = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr;           // copy streams of the pipelined host entry point
+  std::vector<cudaEvent_t> pipe_ev;                        // cached events for it
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tfree; // recycled event pairs
   std::map<std::string, std::pair<void*, size_t>> pool;   // grow-only named device buffers
@@ -112,6 +114,9 @@ int bfl_ctx_destroy(bfl_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->pool)
     if (kv.second.first) cudaFree(kv.second.first);
+  for (auto ev : c->pipe_ev) cudaEventDestroy(ev);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   for (auto& pr : c->tfree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -339,6 +344,8 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;
   if ((rc = c->get("halflogv", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.halflogv = (double*)ptr;
   if ((rc = c->get("uconst", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.uconst = (double*)ptr;
+  if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)sc.NC, &ptr))) return rc;
+  sc.tile_counters = (unsigned long long*)ptr;
   sc.dw = sc.uu = nullptr;
   if (need_general) {
     if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
@@ -425,16 +432,64 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
   if (k0 < 0 || k1 > N || k0 >= k1) return fail(BFL_ERR_ARG, "bad sample range");
   CK(cudaSetDevice(c->device));
   const bool cv = (cle == nullptr) || rows_constant(cle, B, N);
+  const int64_t nk = k1 - k0;
   const size_t nb = sizeof(double) * (size_t)B * N;
+  const size_t nbo = sizeof(double) * (size_t)B * (size_t)nk;
   void *d_clc, *d_cle = nullptr, *d_sk, *d_lnO, *d_marg = nullptr;
   int rc;
   if ((rc = c->get("in_clc", nb, &d_clc))) return rc;
   if (cle && (rc = c->get("in_cle", nb, &d_cle))) return rc;
   if ((rc = c->get("in_sk", sizeof(double) * (size_t)B, &d_sk))) return rc;
-  const size_t nbo = sizeof(double) * (size_t)B * (size_t)(k1 - k0);
   if ((rc = c->get("out_lnO", nbo, &d_lnO))) return rc;
   if (out_marg && (rc = c->get("out_marg", nbo * (size_t)(p->pv.nhyp + 1), &d_marg))) return rc;
   cudaStream_t s = c->stream;
+
+  // Large batches are pipelined in sub-batches of curves: host->device copies, the kernels and
+  // the device->host copies of consecutive sub-batches overlap on three streams (the copy
+  // engines are idle otherwise: 36 MB each way for 1,024 x 4,400 samples).
+  // Sub-batch sizes 1:3:3:1 -- small first and last pieces keep the exposed copy-in / copy-out short,
+  // large middle pieces keep the kernel's tail (one ~100 us warp tile) a small fraction of its run.
+  int nsub = 1;
+  if (!out_marg && B >= 512) nsub = 4;
+  else if (!out_marg && B >= 256) nsub = 2;
+  if (nsub > 1) {
+    if (!c->s_in) CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    if (!c->s_out) CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    while ((int)c->pipe_ev.size() < 2 * nsub + 1) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c->pipe_ev.push_back(ev);
+    }
+    // scratch sized once for the largest sub-batch so nothing is reallocated mid-pipeline
+    CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(c->pipe_ev[2 * nsub], s));
+    CK(cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * nsub], 0));   // previous users of the input buffers are done
+    std::vector<int> lo(nsub + 1);
+    if (nsub == 4) { lo[0] = 0; lo[1] = B / 8; lo[2] = B / 2; lo[3] = B - B / 8; lo[4] = B; }
+    else for (int j = 0; j <= nsub; j++) lo[j] = (int)((int64_t)B * j / nsub);
+    for (int j = 0; j < nsub; j++) {
+      const size_t off = (size_t)lo[j] * N, cnt = (size_t)(lo[j + 1] - lo[j]) * N;
+      CK(cudaMemcpyAsync((double*)d_clc + off, clc + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->s_in));
+      if (cle) CK(cudaMemcpyAsync((double*)d_cle + off, cle + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->s_in));
+      CK(cudaEventRecord(c->pipe_ev[j], c->s_in));
+    }
+    for (int j = 0; j < nsub; j++) {
+      const int Bj = lo[j + 1] - lo[j];
+      const size_t off = (size_t)lo[j] * N, ooff = (size_t)lo[j] * nk;
+      CK(cudaStreamWaitEvent(s, c->pipe_ev[j], 0));
+      SeriesView sv{(const double*)d_clc + off, cle ? (const double*)d_cle + off : nullptr, (const double*)d_sk + lo[j],
+                    Bj, N, 0, N, k0, k1, cv ? 1 : 0};
+      if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO + ooff, nullptr))) return rc;
+      CK(cudaEventRecord(c->pipe_ev[nsub + j], s));
+      CK(cudaStreamWaitEvent(c->s_out, c->pipe_ev[nsub + j], 0));
+      CK(cudaMemcpyAsync(out_lnO + ooff, (double*)d_lnO + ooff, sizeof(double) * (size_t)Bj * nk, cudaMemcpyDeviceToHost,
+                         c->s_out));
+    }
+    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaStreamSynchronize(s));
+    return BFL_OK;
+  }
+
   CK(cudaMemcpyAsync(d_clc, clc, nb, cudaMemcpyHostToDevice, s));
   if (cle) CK(cudaMemcpyAsync(d_cle, cle, nb, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));

@@ -29,6 +29,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace bfl {
 
@@ -248,8 +249,10 @@ cudaError_t launch_plan_orthonormalise(const double* d_raw, const double* d_qb, 
 // per-launch preparation: per-curve scalars and (general path) whitened series
 // ======================================================================================
 __global__ void k_prep_scalars(const double* __restrict__ sk, const double* __restrict__ cle, int64_t seglen,
-                               int B, double* sqrtu, double* halflogv, double* uconst) {
+                               int B, double* sqrtu, double* halflogv, double* uconst,
+                               unsigned long long* tile_counters, int ncounters) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < ncounters) tile_counters[b] = 0ULL;   // dynamic tile scheduler of the window kernel
   if (b >= B) return;
   const double s = sk[b];
   const double e = cle ? cle[(size_t)b * seglen] : 0.0;
@@ -274,7 +277,8 @@ __global__ void k_prep_whiten(const double* __restrict__ clc, const double* __re
 }
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st) {
-  k_prep_scalars<<<(sv.B + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv, sc.uconst);
+  k_prep_scalars<<<(std::max(sv.B, sc.NC) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
+                                                                   sc.uconst, sc.tile_counters, sc.NC);
   st->launches++;
   if (need_general) {
     const int64_t n = sv.seglen * sv.B;
@@ -294,6 +298,7 @@ struct FastArgs {
   int64_t seglen, N, seg0, k0, k1;
   int B, tiles_per_curve;   // tiles_per_curve: warp tiles (32*KT samples) per light curve
   int64_t total_wtiles;
+  unsigned long long* tile_counters;   // [NC] next warp tile to hand out, per template chunk
   const double* hat;      // [G][WP]
   const double* Kg;       // [G]
   const double* lp;       // [G]
@@ -354,7 +359,6 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   const int W = (WT > 0) ? WT : a.W;
   const int H = W / 2;
   const int WP = a.WP;
-  constexpr int WPB = FAST_TPB / 32;             // warps per block
   constexpr int TKW = 32 * KT;                   // samples per warp tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = blockIdx.y;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   const int wstride = (TKW + 2 * H + 2) & ~1;    // doubles per warp slice
 
   double* sdata = smem;                                  // [WPB][wstride]
-  double* stmpl = smem + WPB * wstride;                  // [gchunk + 1][WP] (last row: zeros)
+  double* stmpl = smem + (FAST_TPB / 32) * wstride;      // [gchunk + 1][WP] (last row: zeros)
   double* sK = stmpl + (size_t)(a.gchunk + 1) * WP;      // [gchunk]  Kg + lp (+ lw)
   double* sphi = sK + ((a.gchunk + 1) & ~1);             // [2][(DEG+1) * NI] phi(z) and z^2/2 tables
   double* st64 = sphi + 2 * BFL_PHI_STRIDE;              // [64] 2^(j/64)
@@ -400,7 +404,13 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   const int64_t nk = a.k1 - a.k0;
   double* swin = sdata + warp * wstride;
 
-  for (int64_t wt = (int64_t)blockIdx.x * WPB + warp; wt < a.total_wtiles; wt += (int64_t)gridDim.x * WPB) {
+  // dynamic scheduling: every warp takes the next warp tile from a global counter, so the
+  // tail is one tile long however the tile count divides among the resident warps
+  for (;;) {
+  long long wt = 0;
+  if (lane == 0) wt = (long long)atomicAdd(a.tile_counters + chunk, 1ULL);
+  wt = __shfl_sync(0xffffffffu, wt, 0);
+  if (wt >= a.total_wtiles) break;
   const int tile = (int)(wt % a.tiles_per_curve);
   const int b = (int)(wt / a.tiles_per_curve);
   const int64_t kbase = a.k0 + (int64_t)tile * TKW;
@@ -805,6 +815,7 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
   const int64_t nk = sv.k1 - sv.k0;
   a.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
   a.total_wtiles = (int64_t)a.tiles_per_curve * sv.B;
+  a.tile_counters = sc.tile_counters;
   a.hat = pv.hat; a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.gorig = pv.gorig;
   a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.gchunk = sc.gchunk; a.NC = sc.NC; a.nhyp = pv.nhyp;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];

@@ -53,6 +53,7 @@ struct Scratch {
   double* uu;      // [B][seglen] v        (general path)
   double2* part;   // [nhyp][NC][B*nk] partial log-sum-exp (max, sum)
   double* bgabs;   // [B*nk] polynomial-only log Bayes factor (no sumlogsigma) or nullptr
+  unsigned long long* tile_counters;  // [NC] dynamic tile scheduler state
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
