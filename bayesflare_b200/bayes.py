@@ -312,8 +312,11 @@ class ParameterEstimationGrid:
         params = np.zeros((int(np.prod(sp)), 4))
         for i, m in enumerate(mesh):
             params[:, i] = m.ravel()
-        pdicts = ({p: pv[p][q[i]] for i, p in enumerate(self.paramNames)} for q in np.ndindex(*sp))
-        logprior = np.array([self.prior(pd) for pd in pdicts], dtype=float)
+        if self.prior == self.model.prior:
+            logprior = self.model.grid_logprior(values=pv)          # vectorised for the built-in models
+        else:
+            pdicts = ({p: pv[p][q[i]] for i, p in enumerate(self.paramNames)} for q in np.ndindex(*sp))
+            logprior = np.array([self.prior(pd) for pd in pdicts], dtype=float)
         polyms = None
         if margbackground:
             ts01 = np.linspace(0, 1, dl)

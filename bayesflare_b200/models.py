@@ -116,9 +116,28 @@ class Model:
             out[:, i] = m.ravel()
         return out
 
-    def grid_logprior(self):
-        G = int(np.prod(self.shape))
-        return np.array([self.prior(self._pdict(q)) for q in range(G)], dtype=float)
+    def grid_logprior(self, values=None):
+        """log prior of every grid point (C order).  ``values`` optionally replaces the parameter
+        axes (``ParameterEstimationGrid`` evaluates the prior on its own grid while the prior's
+        normalisation comes from ``self.ranges``, as the reference does).  Built-in models override
+        :meth:`_logprior_mesh` with a vectorised form; this generic version calls ``prior`` per point."""
+        axes = [np.asarray((values or self.ranges)[p]) for p in self.paramnames]
+        fast = self._logprior_mesh(dict(zip(self.paramnames, np.meshgrid(*axes, indexing="ij"))))
+        if fast is not None:
+            return np.asarray(fast, dtype=float).ravel()
+        shape = [len(a) for a in axes]
+        out = np.empty(int(np.prod(shape)))
+        for q in range(out.size):
+            idx = np.unravel_index(q, shape)
+            out[q] = self.prior({p: axes[i][idx[i]] for i, p in enumerate(self.paramnames)})
+        return out
+
+    def _logprior_mesh(self, mesh):
+        """Vectorised ``prior`` over a dict of broadcast parameter arrays, or ``None``."""
+        return None
+
+    def _flat_total(self):
+        return sum(_flat_logprior(self.ranges[p]) for p in self.paramnames)
 
     def grid_logweight(self):
         """log of the product trapezium weight of every grid point: marginalising each
@@ -191,6 +210,21 @@ class Flare(Model):
         return base + (-np.log(area))
 
 
+def _flare_logprior_mesh(self, mesh):
+    # same value as Flare.prior for every point: constant inside the allowed region, -inf outside
+    tg, te = np.asarray(mesh['taugauss'], dtype=float), np.asarray(mesh['tauexp'], dtype=float)
+    bad = (tg > te) | (tg > self.ranges['tauexp'][-1])
+    out = np.full(tg.shape, -np.inf)
+    if not bad.all():
+        i = np.argmin(bad.ravel())
+        ok = self.prior({p: np.asarray(mesh[p]).ravel()[i] for p in self.paramnames})
+        out[~bad] = ok
+    return out
+
+
+Flare._logprior_mesh = _flare_logprior_mesh
+
+
 class Transit(Model):
     """Flat-bottomed transit with Gaussian wings (model.py:332-517)."""
     device_kind = "transit"
@@ -254,6 +288,19 @@ class Transit(Model):
         return ampp + t0p + lntf + lnsg
 
 
+def _transit_logprior_mesh(self, mesh):
+    sg, tf = np.asarray(mesh['sigmag'], dtype=float), np.asarray(mesh['tauf'], dtype=float)
+    bad = (tf + 2. * 3. * sg) > self.maxdur
+    out = np.full(sg.shape, -np.inf)
+    if not bad.all():
+        i = np.argmin(bad.ravel())
+        out[~bad] = self.prior({p: np.asarray(mesh[p]).ravel()[i] for p in self.paramnames})
+    return out
+
+
+Transit._logprior_mesh = _transit_logprior_mesh
+
+
 class Expdecay(Model):
     """Pure exponential decay, or rise when reversed (model.py:520-652)."""
     device_kind = "expdecay"
@@ -284,6 +331,14 @@ class Expdecay(Model):
     def prior(self, pdict):
         self._need(pdict)
         return sum(_flat_logprior(self.ranges[p]) for p in ('t0', 'amp', 'tauexp'))
+
+
+def _flat_logprior_mesh(self, mesh):
+    first = next(iter(mesh.values()))
+    return np.full(np.shape(first), self._flat_total())
+
+
+Expdecay._logprior_mesh = _flat_logprior_mesh
 
 
 class Impulse(Model):
@@ -363,3 +418,8 @@ class Step(Model):
     def prior(self, pdict):
         self._need(pdict)
         return _flat_logprior(self.ranges['t0']) + _flat_logprior(self.ranges['amp'])
+
+
+Impulse._logprior_mesh = _flat_logprior_mesh
+Step._logprior_mesh = _flat_logprior_mesh
+Gaussian._logprior_mesh = _flat_logprior_mesh
