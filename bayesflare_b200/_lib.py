@@ -31,6 +31,32 @@ class Hypothesis(C.Structure):
                 ("params", _dp), ("logprior", _dp), ("logweight", _dp), ("table", _dp)]
 
 
+class NoiseSpec(C.Structure):
+    _fields_ = [("method", C.c_int32), ("bglen", C.c_int32), ("param", C.c_double), ("sgcoef", _dp)]
+
+
+NOISE_METHODS = {"powerspectrum": 0, "tailveto": 1}
+
+
+def make_noise_spec(method, bglen, bgorder, psestfrac=0.5, tvsigma=1.0, detrended=False):
+    """``bfl_noise_spec`` for the reference's noise estimate (bayes.py:235-246).  Returns the
+    structure and the arrays that must stay alive while it is in use."""
+    from .noise import _sg_coefficients
+    if method not in NOISE_METHODS:
+        raise ValueError("Noise estimation method must be 'powerspectrum' or 'tailveto'")
+    spec = NoiseSpec()
+    spec.method = NOISE_METHODS[method]
+    coef = None
+    if detrended:
+        spec.bglen = 0
+    else:
+        coef = f64(_sg_coefficients(int(bglen), int(bgorder)))
+        spec.bglen = int(bglen)
+        spec.sgcoef = ptr(coef)
+    spec.param = float(psestfrac if method == "powerspectrum" else tvsigma)
+    return spec, coef
+
+
 # every symbol include/bfl.h declares: (restype, argtypes)
 SIGNATURES = {
     "bfl_version": (C.c_int, []),
@@ -49,8 +75,10 @@ SIGNATURES = {
     "bfl_plan_templates": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "bfl_window_lnB": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int64, C.c_double,
                                  _dp, _dp]),
-    "bfl_detector_odds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int32, C.c_int64, C.c_int64,
-                                    C.c_int64, _dp, _dp]),
+    "bfl_noise_sigma": (C.c_int, [C.c_void_p, C.POINTER(NoiseSpec), _dp, C.c_int32, C.c_int64, _dp]),
+    "bfl_noise_sigma_dev": (C.c_int, [C.c_void_p, C.POINTER(NoiseSpec), C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
+    "bfl_detector_odds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, _dp, C.POINTER(NoiseSpec), C.c_int32,
+                                    C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp]),
     "bfl_detector_odds_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_void_p]),
@@ -201,25 +229,40 @@ class Plan:
                                       float(sk), N, float(sumlogsigma), ptr(out), ptr(bg)))
         return out, bg
 
-    def detector_odds(self, clc, cle, sk, noisepoly=True, want_marg=False, k0=0, k1=None):
-        """Log odds for samples [k0, k1) of every curve (default: all N samples)."""
+    def detector_odds(self, clc, cle, sk, noisepoly=True, want_marg=False, k0=0, k1=None, noise=None,
+                      want_sk=False):
+        """Log odds for samples [k0, k1) of every curve (default: all N samples).  With ``sk=None`` the
+        noise sigma of every curve is estimated on the device as ``noise`` (a :func:`make_noise_spec`
+        result) describes; ``want_sk`` returns the sigmas used as the last element."""
         clc = f64(clc)
         single = clc.ndim == 1
         clc = np.atleast_2d(clc)
         B, N = clc.shape
         cle = None if cle is None else np.atleast_2d(f64(cle))
-        sk = f64(np.atleast_1d(sk))
-        if sk.size != B or (cle is not None and cle.shape != clc.shape):
-            raise ValueError("batch shapes of clc, cle and sk do not agree")
+        spec = None
+        if sk is None:
+            if noise is None:
+                raise ValueError("either sk or a noise specification is required")
+            spec = C.byref(noise[0])
+        else:
+            sk = f64(np.atleast_1d(sk))
+            if sk.size != B:
+                raise ValueError("batch shapes of clc and sk do not agree")
+        if cle is not None and cle.shape != clc.shape:
+            raise ValueError("batch shapes of clc and cle do not agree")
         k1 = N if k1 is None else int(k1)
         lnO = np.empty((B, k1 - k0))
         marg = np.empty((self.nhyp + 1, B, k1 - k0)) if want_marg else None
+        sk_out = np.empty(B) if want_sk else None
         check(self.lib.bfl_detector_odds(self.ctx.handle, self.handle, 1 if noisepoly else 0, ptr(clc), ptr(cle),
-                                         ptr(sk), B, N, int(k0), k1, ptr(lnO), ptr(marg)))
+                                         ptr(sk), spec, B, N, int(k0), k1, ptr(lnO), ptr(marg), ptr(sk_out)))
         if single:
             lnO = lnO[0]
             marg = None if marg is None else marg[:, 0]
-        return (lnO, marg) if want_marg else lnO
+        out = (lnO, marg) if want_marg else (lnO,)
+        if want_sk:
+            out = out + (sk_out,)
+        return out if len(out) > 1 else out[0]
 
     def detector_odds_dev(self, d_clc, d_cle, const_var, d_sk, B, N, seg0, seglen, k0, k1, d_lnO, noisepoly=True):
         """Device-resident, asynchronous variant: arguments are raw device addresses (ints)."""
@@ -237,6 +280,15 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def noise_sigma(ctx, clc, spec):
+    """Noise sigma of every curve of ``clc[B, N]`` on the device (``bfl_noise_sigma``)."""
+    clc = np.atleast_2d(f64(clc))
+    B, N = clc.shape
+    out = np.empty(B)
+    check(ctx.lib.bfl_noise_sigma(ctx.handle, C.byref(spec[0]), ptr(clc), B, N, ptr(out)))
+    return out
 
 
 def threshold(ctx, lnO, thresh, expand=0):

@@ -27,6 +27,10 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def cuda_lib_dir() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc_path()))), "lib64")
+
+
 def up_to_date() -> bool:
     if not os.path.exists(LIB):
         return False
@@ -45,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-shared",
            "-I", os.path.join(ROOT, "include"),
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcufft", "-Xlinker", "-rpath=" + cuda_lib_dir()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

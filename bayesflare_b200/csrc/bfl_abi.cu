@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <cufft.h>
+
 using namespace bfl;
 
 static thread_local std::string g_err;
@@ -44,6 +46,7 @@ struct bfl_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tfree; // recycled event pairs
   std::map<std::string, std::pair<void*, size_t>> pool;   // grow-only named device buffers
+  std::map<std::pair<int64_t, int>, cufftHandle> fft;     // cached batched D2Z plans keyed by (N, batch)
 
   int get(const char* name, size_t bytes, void** out) {
     auto& e = pool[name];
@@ -114,6 +117,7 @@ int bfl_ctx_destroy(bfl_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& kv : c->pool)
     if (kv.second.first) cudaFree(kv.second.first);
+  for (auto& kv : c->fft) cufftDestroy(kv.second);
   for (auto ev : c->pipe_ev) cudaEventDestroy(ev);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -414,6 +418,77 @@ int bfl_detector_odds_dev(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* 
   return detector_run(c, p, noisepoly, sv, d_lnO, nullptr);
 }
 
+
+// --------------------------------------------------------------------------------------
+// noise sigma on device
+static int noise_run(bfl_ctx* c, const bfl_noise_spec* spec, const double* d_clc, int B, int64_t N, double* d_sk) {
+  if (!spec) return fail(BFL_ERR_ARG, "noise specification is null");
+  if (spec->method != 0 && spec->method != 1) {   // bayes.py:243-245
+    return fail(BFL_ERR_ARG, "Noise estimation method must be 'powerspectrum' or 'tailveto'");
+  }
+  if (spec->bglen != 0 && (spec->bglen < 3 || spec->bglen % 2 == 0 || !spec->sgcoef || spec->bglen > MAXW))
+    return fail(BFL_ERR_ARG, "window_size size must be a positive odd number");
+  if (N < 4 || (spec->bglen && N <= spec->bglen)) return fail(BFL_ERR_ARG, "light curve too short for the noise estimate");
+  if (spec->method == 0 && !(spec->param > 0.0 && spec->param <= 1.0)) return fail(BFL_ERR_ARG, "psestfrac must be in (0, 1]");
+  if (spec->method == 1 && !(spec->param > 0.0)) return fail(BFL_ERR_ARG, "tvsigma must be positive");
+  cudaStream_t s = c->stream;
+  int rc;
+  void* ptr;
+  const double* d_res = d_clc;
+  if (spec->bglen) {
+    void* d_m;
+    if ((rc = c->get("sg_coef", sizeof(double) * MAXW, &d_m))) return rc;
+    if ((rc = c->get("sg_resid", sizeof(double) * (size_t)B * N, &ptr))) return rc;
+    CK(cudaMemcpyAsync(d_m, spec->sgcoef, sizeof(double) * (size_t)spec->bglen, cudaMemcpyHostToDevice, s));
+    CK(launch_sg_resid(d_clc, N, B, (const double*)d_m, spec->bglen, (double*)ptr, s, &c->stats));
+    d_res = (const double*)ptr;
+  }
+  if (spec->method == 0) {
+    const int64_t L = N / 2 + 1;
+    if ((rc = c->get("fft_out", sizeof(double2) * (size_t)B * L, &ptr))) return rc;
+    auto key = std::make_pair(N, B);
+    auto it = c->fft.find(key);
+    if (it == c->fft.end()) {
+      cufftHandle plan;
+      int n[1] = {(int)N};
+      cufftResult r = cufftPlanMany(&plan, 1, n, nullptr, 1, (int)N, nullptr, 1, (int)L, CUFFT_D2Z, B);
+      if (r != CUFFT_SUCCESS) return fail(BFL_ERR_CUDA, "cufftPlanMany failed (" + std::to_string((int)r) + ")");
+      it = c->fft.emplace(key, plan).first;
+    }
+    if (cufftSetStream(it->second, s) != CUFFT_SUCCESS) return fail(BFL_ERR_CUDA, "cufftSetStream failed");
+    cufftResult r = cufftExecD2Z(it->second, (cufftDoubleReal*)d_res, (cufftDoubleComplex*)ptr);
+    if (r != CUFFT_SUCCESS) return fail(BFL_ERR_CUDA, "cufftExecD2Z failed (" + std::to_string((int)r) + ")");
+    c->stats.launches++;
+    CK(launch_ps_sigma((const double2*)ptr, N, B, spec->param, d_sk, s, &c->stats));
+  } else {
+    void *d_cnt, *d_rng;
+    if ((rc = c->get("tv_counts", sizeof(int) * (size_t)B * N, &d_cnt))) return rc;
+    if ((rc = c->get("tv_range", sizeof(double) * 2 * (size_t)B, &d_rng))) return rc;
+    CK(launch_tv_sigma(d_res, N, B, spec->param, (int*)d_cnt, (double*)d_rng, d_sk, s, &c->stats));
+  }
+  return BFL_OK;
+}
+
+int bfl_noise_sigma_dev(bfl_ctx* c, const bfl_noise_spec* spec, const double* d_clc, int32_t B, int64_t N, double* d_sk) {
+  if (!c || !d_clc || !d_sk || B < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_noise_sigma_dev");
+  CK(cudaSetDevice(c->device));
+  return noise_run(c, spec, d_clc, B, N, d_sk);
+}
+
+int bfl_noise_sigma(bfl_ctx* c, const bfl_noise_spec* spec, const double* clc, int32_t B, int64_t N, double* out_sk) {
+  if (!c || !clc || !out_sk || B < 1 || N < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_noise_sigma");
+  CK(cudaSetDevice(c->device));
+  void *d_clc, *d_sk;
+  int rc;
+  if ((rc = c->get("in_clc", sizeof(double) * (size_t)B * N, &d_clc))) return rc;
+  if ((rc = c->get("in_sk", sizeof(double) * (size_t)B, &d_sk))) return rc;
+  CK(cudaMemcpyAsync(d_clc, clc, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = noise_run(c, spec, (const double*)d_clc, B, N, (double*)d_sk))) return rc;
+  CK(cudaMemcpyAsync(out_sk, d_sk, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return BFL_OK;
+}
+
 static bool rows_constant(const double* a, int B, int64_t N) {
   for (int b = 0; b < B; b++) {
     const double* r = a + (size_t)b * N;
@@ -425,9 +500,10 @@ static bool rows_constant(const double* a, int B, int64_t N) {
 }
 
 int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc, const double* cle,
-                      const double* sk, int32_t B, int64_t N, int64_t k0, int64_t k1, double* out_lnO,
-                      double* out_marg) {
-  if (!c || !p || !clc || !sk || !out_lnO) return fail(BFL_ERR_ARG, "null argument to bfl_detector_odds");
+                      const double* sk, const bfl_noise_spec* noise, int32_t B, int64_t N, int64_t k0, int64_t k1,
+                      double* out_lnO, double* out_marg, double* out_sk) {
+  if (!c || !p || !clc || !out_lnO) return fail(BFL_ERR_ARG, "null argument to bfl_detector_odds");
+  if (!sk && !noise) return fail(BFL_ERR_ARG, "either the noise sigmas or a noise specification is required");
   if (B < 1 || N < 1) return fail(BFL_ERR_ARG, "empty batch");
   if (k0 < 0 || k1 > N || k0 >= k1) return fail(BFL_ERR_ARG, "bad sample range");
   CK(cudaSetDevice(c->device));
@@ -461,7 +537,7 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
       c->pipe_ev.push_back(ev);
     }
     // scratch sized once for the largest sub-batch so nothing is reallocated mid-pipeline
-    CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+    if (sk) CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(c->pipe_ev[2 * nsub], s));
     CK(cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * nsub], 0));   // previous users of the input buffers are done
     std::vector<int> lo(nsub + 1);
@@ -477,6 +553,7 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
       const int Bj = lo[j + 1] - lo[j];
       const size_t off = (size_t)lo[j] * N, ooff = (size_t)lo[j] * nk;
       CK(cudaStreamWaitEvent(s, c->pipe_ev[j], 0));
+      if (!sk && (rc = noise_run(c, noise, (const double*)d_clc + off, Bj, N, (double*)d_sk + lo[j]))) return rc;
       SeriesView sv{(const double*)d_clc + off, cle ? (const double*)d_cle + off : nullptr, (const double*)d_sk + lo[j],
                     Bj, N, 0, N, k0, k1, cv ? 1 : 0};
       if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO + ooff, nullptr))) return rc;
@@ -485,6 +562,7 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
       CK(cudaMemcpyAsync(out_lnO + ooff, (double*)d_lnO + ooff, sizeof(double) * (size_t)Bj * nk, cudaMemcpyDeviceToHost,
                          c->s_out));
     }
+    if (out_sk) CK(cudaMemcpyAsync(out_sk, d_sk, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(c->s_out));
     CK(cudaStreamSynchronize(s));
     return BFL_OK;
@@ -492,7 +570,9 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
 
   CK(cudaMemcpyAsync(d_clc, clc, nb, cudaMemcpyHostToDevice, s));
   if (cle) CK(cudaMemcpyAsync(d_cle, cle, nb, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+  if (sk) CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+  else if ((rc = noise_run(c, noise, (const double*)d_clc, B, N, (double*)d_sk))) return rc;
+  if (out_sk) CK(cudaMemcpyAsync(out_sk, d_sk, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
   SeriesView sv{(const double*)d_clc, (const double*)d_cle, (const double*)d_sk, B, N, 0, N, k0, k1, cv ? 1 : 0};
   if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO, (double*)d_marg))) return rc;
   CK(cudaMemcpyAsync(out_lnO, d_lnO, nbo, cudaMemcpyDeviceToHost, s));

@@ -1660,6 +1660,175 @@ cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int ns
   return cudaGetLastError();
 }
 
+
+// ======================================================================================
+// noise-sigma estimation on device: noise/noise.py:10-103, 176-252,
+// data/data.py:184-203, 377-409, stats/bayes.py:235-246
+// ======================================================================================
+// Savitzky-Golay detrend: resid = y - fit, fit[i] = sum_j m[j] * ypad[i + j], with the reference's
+// mirrored-difference edge padding (noise.py:247-251).  m = pinv(b)[0] comes from the caller.
+__global__ void k_sg_resid(const double* __restrict__ y, int64_t N, int B, const double* __restrict__ m, int W,
+                           double* __restrict__ resid) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * B) return;
+  const int b = (int)(idx / N);
+  const int64_t i = idx - (int64_t)b * N;
+  const double* yy = y + (size_t)b * N;
+  const int h = (W - 1) / 2;
+  const double y0 = yy[0], yl = yy[N - 1];
+  double fit = 0.0;
+  for (int j = 0; j < W; j++) {
+    const int64_t t = i + j;          // index into the padded series
+    double v;
+    if (t < h) v = y0 - fabs(yy[h - t] - y0);
+    else if (t < h + N) v = yy[t - h];
+    else v = yl + fabs(yy[N - 2 - (t - h - N)] - yl);
+    fit = fma(m[j], v, fit);
+  }
+  resid[idx] = yy[i] - fit;
+}
+
+// 'powerspectrum' estimator: sigma^2 = mean of the upper `estfrac` of the one-sided periodogram
+// times fs/2 (noise.py:36-40) = sum_k c_k |X_k|^2 / (2 n cnt), c_k = 2 except DC and Nyquist.
+__global__ void __launch_bounds__(256) k_ps_sigma(const double2* __restrict__ X, int64_t N, int64_t L, int64_t k0,
+                                                  double* __restrict__ sk) {
+  const int b = blockIdx.x;
+  const double2* x = X + (size_t)b * L;
+  double s = 0.0;
+  for (int64_t k = k0 + threadIdx.x; k < L; k += 256) {
+    const double2 v = x[k];
+    const double p = fma(v.x, v.x, v.y * v.y);
+    const bool single = (k == 0) || ((N % 2 == 0) && (k == N / 2));
+    s += single ? p : 2.0 * p;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sk[b] = sqrt(red[0] / (2.0 * (double)N * (double)(L - k0)));
+}
+
+// 'tailveto' estimator, part 1: N-bin histogram of one curve with NumPy's bin assignment
+// (numpy.histogram uniform-bin path incl. its one-ulp edge corrections), one block per curve.
+__device__ __forceinline__ double tv_edge(int64_t i, int64_t N, double lo, double hi, double step) {
+  return (i == N) ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);    // np.linspace: arange*step + start, last = stop
+}
+
+__global__ void __launch_bounds__(256) k_tv_hist(const double* __restrict__ d, int64_t N, int* __restrict__ counts,
+                                                 double* __restrict__ range) {
+  const int b = blockIdx.x;
+  const double* x = d + (size_t)b * N;
+  __shared__ double smin[256], smax[256];
+  double mn = INFINITY, mx = -INFINITY;
+  bool bad = false;
+  for (int64_t i = threadIdx.x; i < N; i += 256) {
+    const double v = x[i];
+    if (!isfinite(v)) bad = true;
+    mn = fmin(mn, v); mx = fmax(mx, v);
+  }
+  smin[threadIdx.x] = bad ? nan("") : mn;
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double a = smin[threadIdx.x], c = smin[threadIdx.x + o];
+      smin[threadIdx.x] = (isnan(a) || isnan(c)) ? nan("") : fmin(a, c);
+      smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  double lo = smin[0], hi = smax[0];
+  if (isnan(lo)) {   // NaN / inf in the data: np.histogram raises; report NaN
+    if (threadIdx.x == 0) { range[2 * b] = nan(""); range[2 * b + 1] = nan(""); }
+    return;
+  }
+  if (lo == hi) { lo -= 0.5; hi += 0.5; }      // numpy _get_outer_edges
+  if (threadIdx.x == 0) { range[2 * b] = lo; range[2 * b + 1] = hi; }
+  const double step = (hi - lo) / (double)N;
+  const double denom = hi - lo;
+  int* c = counts + (size_t)b * N;
+  for (int64_t i = threadIdx.x; i < N; i += 256) {
+    const double v = x[i];
+    int64_t idx = (int64_t)(__dmul_rn(__ddiv_rn(v - lo, denom), (double)N));
+    if (idx == N) idx -= 1;
+    if (v < tv_edge(idx, N, lo, hi, step)) idx -= 1;
+    if (v >= tv_edge(idx + 1, N, lo, hi, step) && idx != N - 1) idx += 1;
+    atomicAdd(c + idx, 1);
+  }
+}
+
+// part 2 (one thread per curve, sequential like np.cumsum): density, cumulative distribution,
+// np.unique + scipy interp1d at 0.5 -/+ cp/2 (noise.py:83-101)
+__global__ void k_tv_finish(const int* __restrict__ counts, const double* __restrict__ range, int64_t N, int B,
+                            double sigma, double cp, double* __restrict__ sk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double lo = range[2 * b], hi = range[2 * b + 1];
+  if (isnan(lo)) { sk[b] = nan(""); return; }
+  const int* c = counts + (size_t)b * N;
+  const double step = (hi - lo) / (double)N;
+  const double w0 = tv_edge(1, N, lo, hi, step) - tv_edge(0, N, lo, hi, step);
+  const double tgt[2] = {0.5 - cp / 2.0, 0.5 + cp / 2.0};
+  double val[2] = {nan(""), nan("")};
+  int state[2] = {0, 0};            // 0 searching, 1 waiting for the second unique point, 2 done
+  double cs = 0.0, xl = 0.0, yl = 0.0, xp = 0.0, yp = 0.0;
+  int nu = 0;
+  double e0 = tv_edge(0, N, lo, hi, step);
+  for (int64_t i = 0; i < N; i++) {
+    const double e1 = tv_edge(i + 1, N, lo, hi, step);
+    const double ni = __ddiv_rn(__ddiv_rn((double)c[i], e1 - e0), (double)N);   // n / db / n.sum()
+    cs = __dadd_rn(cs, __dmul_rn(ni, w0));
+    if (nu == 0 || cs != xl) {       // a new unique value of the cumulative distribution (first index kept)
+      xp = xl; yp = yl;
+      xl = cs; yl = (e0 + e1) / 2.0;
+      nu++;
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        if (state[t] == 1) {           // target sits at/below the first point: interpolate on points 0 and 1
+          val[t] = (yl - yp) / (xl - xp) * (tgt[t] - xp) + yp;
+          state[t] = 2;
+        } else if (state[t] == 0 && xl >= tgt[t]) {
+          if (nu == 1) state[t] = (tgt[t] < xl) ? 3 : 1;     // below the interpolation range -> error
+          else { val[t] = (yl - yp) / (xl - xp) * (tgt[t] - xp) + yp; state[t] = 2; }
+        }
+      }
+    }
+    e0 = e1;
+  }
+  sk[b] = (state[0] == 2 && state[1] == 2) ? (val[1] - val[0]) / (2.0 * sigma) : nan("");
+}
+
+cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
+                            cudaStream_t s, LaunchStats* st) {
+  const int64_t n = N * B;
+  k_sg_resid<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_y, N, B, d_m, W, d_resid);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ps_sigma(const double2* d_X, int64_t N, int B, double estfrac, double* d_sk, cudaStream_t s,
+                            LaunchStats* st) {
+  const int64_t L = N / 2 + 1;
+  const int64_t k0 = (int64_t)floor((1.0 - estfrac) * (double)L);
+  k_ps_sigma<<<B, 256, 0, s>>>(d_X, N, L, k0, d_sk);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tv_sigma(const double* d_resid, int64_t N, int B, double sigma, int* d_counts, double* d_range,
+                            double* d_sk, cudaStream_t s, LaunchStats* st) {
+  cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)N * B, s);
+  if (e != cudaSuccess) return e;
+  k_tv_hist<<<B, 256, 0, s>>>(d_resid, N, d_counts, d_range);
+  st->launches++;
+  k_tv_finish<<<(B + 31) / 32, 32, 0, s>>>(d_counts, d_range, N, B, sigma, erf(sigma / sqrt(2.0)), d_sk);
+  st->launches++;
+  return cudaGetLastError();
+}
+
 // ======================================================================================
 // FP64 FMA throughput probe: 16 independent chains per thread
 // ======================================================================================

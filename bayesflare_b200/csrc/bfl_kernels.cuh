@@ -101,6 +101,12 @@ cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int ns
 
 cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
                                  cudaStream_t s, LaunchStats* st);
+cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
+                            cudaStream_t s, LaunchStats* st);
+cudaError_t launch_ps_sigma(const double2* d_X, int64_t N, int B, double estfrac, double* d_sk, cudaStream_t s,
+                            LaunchStats* st);
+cudaError_t launch_tv_sigma(const double* d_resid, int64_t N, int B, double sigma, int* d_counts, double* d_range,
+                            double* d_sk, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
 
 size_t fast_smem_bytes(int W, int gchunk, int KT);

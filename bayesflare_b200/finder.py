@@ -205,19 +205,30 @@ class OddsRatioDetector:
             lnO = lnO + float(np.sum(np.log(np.sqrt(noisevar))))
         return list(lnO), np.copy(lc.cts[h:N - h])
 
-    def oddsratio_batch(self, clc, sk=None, cle=None):
+    def noise_spec(self, detrended=False):
+        """Device-side description of this detector's noise estimate (``bfl_noise_spec``)."""
+        return _lib.make_noise_spec(self.noiseestmethod, self.bglen, self.bgorder,
+                                    psestfrac=self.psestfrac if self.psestfrac is not None else 0.5,
+                                    tvsigma=self.tvsigma if self.tvsigma is not None else 1.0, detrended=detrended)
+
+    def noise_sigma_batch(self, clc):
+        """Noise sigma of every curve of ``clc[B, N]``, estimated on the device with the same
+        algorithm as :meth:`noise_sigma` (Savitzky-Golay detrend + power spectrum / tail veto)."""
+        return _lib.noise_sigma(_lib.default_context(self.device), clc, self.noise_spec())
+
+    def oddsratio_batch(self, clc, sk=None, cle=None, return_sk=False):
         """Extension: log odds for a batch ``clc[B, N]`` of light curves that share this detector's
-        time base and configuration, in one launch.  ``sk[B]`` are the noise sigmas (estimated per
-        curve when omitted).  Returns an array ``[B, N']`` (edges dropped when ``ignoreedges``)."""
+        time base and configuration.  ``sk[B]`` are the noise sigmas; when omitted they are estimated
+        on the device from the uploaded curves, so the whole ``oddsratio`` pipeline of the reference
+        (noise estimate, every hypothesis, marginalisation, combination) runs on the GPU.
+        Returns an array ``[B, N']`` (edges dropped when ``ignoreedges``)."""
         clc = np.atleast_2d(np.asarray(clc, dtype=float))
         B, N = clc.shape
         plan = self.plan()
-        if sk is None:
-            from .lightcurve import Lightcurve
-            sk = np.array([self.noise_sigma(Lightcurve(cts=self.lightcurve.cts, clc=clc[b],
-                                                       cle=None if cle is None else cle[b])) for b in range(B)])
         h = int(self.bglen / 2) if self.ignoreedges else 0
-        return plan.detector_odds(clc, cle, sk, noisepoly=self.noisepoly, k0=h, k1=N - h)
+        noise = self.noise_spec() if sk is None else None
+        return plan.detector_odds(clc, cle, sk, noisepoly=self.noisepoly, k0=h, k1=N - h, noise=noise,
+                                  want_sk=return_sk)
 
     # ---- post-processing (find.py:866-1019) -----------------------------------------------
     def impulse_excluder(self, lnO, ts, exclusionwidth=5):

@@ -199,10 +199,10 @@ def run_ours(args, rank, local_rank, world):
                      [hypothesis_from_model(m, mts, hr) for m, hr in models])
     g_eval = int(sum(np.isfinite(hypothesis_from_model(m, mts, hr)["logprior"]).sum() for m, hr in models)) + 1
     assert g_eval == G_EVAL, g_eval
-    # noise sigma per curve: host-side estimator of the reference (bayes.py:235-246), input to the C ABI
-    t_sk = time.perf_counter()
-    sk = np.array([det.noise_sigma(bf.Lightcurve(cts=cts, clc=clc0[b])) for b in range(B)])
-    t_sk = time.perf_counter() - t_sk
+    # noise sigma per curve (bayes.py:235-246), estimated on the device (bfl_noise_sigma); the
+    # device-resident `value` loop takes it as an input, the e2e loop re-estimates it every step
+    noise_spec = det.noise_spec()
+    sk = _lib.noise_sigma(ctx, clc0, noise_spec)
 
     host = [torch.from_numpy(clc0).pin_memory()]
     for i in range(1, NB):
@@ -277,10 +277,12 @@ def run_ours(args, rank, local_rank, world):
     dp = C.POINTER(C.c_double)
 
     def e2e_step(i):
+        # everything OddsRatioDetector.oddsratio does for a batch, from host memory to host memory:
+        # H2D, noise sigma per curve (sk = NULL -> estimated on device), all hypotheses, D2H
         j = i % NB
         _lib.check(lib.bfl_detector_odds(ctx.handle, plan.handle, 1, C.cast(host[j].data_ptr(), dp), None,
-                                         sk_rolled[j].ctypes.data_as(dp), B, N, K0, K1,
-                                         C.cast(out_host.data_ptr(), dp), None))
+                                         None, C.byref(noise_spec[0]), B, N, K0, K1,
+                                         C.cast(out_host.data_ptr(), dp), None, None))
     for i in range(max(2, args.warmup // 2)):
         e2e_step(i)
     torch.cuda.synchronize()
@@ -340,8 +342,8 @@ def run_ours(args, rank, local_rank, world):
                        "parallelism": "dp%d (one batch per rank, no data-path collective)" % world},
             "e2e": {"value": e2e_value, "unit": "samples*grid-points/s", "h2d_bytes_per_step": B * N * 8 + B * 8,
                     "d2h_bytes_per_step": B * NK * 8, "steps": e2e_steps,
-                    "what": "bfl_detector_odds (C ABI) with pinned host buffers; noise sigma per curve is an input "
-                            "(host estimator took %.2f s for the batch, outside the timed region)" % t_sk},
+                    "what": "bfl_detector_odds (C ABI) with pinned host buffers: H2D, noise sigma of every curve "
+                            "estimated on device (SG detrend + periodogram), all hypotheses, D2H of the log odds"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -104,11 +104,31 @@ int bfl_plan_templates(bfl_plan* plan, int ihyp, double* out);
 int bfl_window_lnB(bfl_ctx* ctx, bfl_plan* plan, int ihyp, const double* clc, const double* cle,
                    double sk, int64_t N, double sumlogsigma, double* out_lnB, double* out_bg);
 
+/* ---- noise sigma on device (the pre-step of bayes.py:235-246) --------------------------
+ * Savitzky-Golay detrend (noise.py:176-252, data.py:377-409) followed by either the
+ * power-spectrum estimator (noise.py:10-44 with Lightcurve.psd, data.py:184-203; the FFT is
+ * cuFFT) or the tail-veto estimator (noise.py:47-103: N-bin histogram CDF, np.unique, interp1d). */
+typedef struct {
+  int32_t method;       /* 0 = 'powerspectrum', 1 = 'tailveto' */
+  int32_t bglen;        /* Savitzky-Golay window length; 0 = the curve is already detrended */
+  double param;         /* psestfrac, or tvsigma */
+  const double* sgcoef; /* host [bglen]: np.linalg.pinv(b)[0] as noise.py:241-245 computes it */
+} bfl_noise_spec;
+
+/* clc host [B][N] -> out_sk host [B] */
+int bfl_noise_sigma(bfl_ctx* ctx, const bfl_noise_spec* spec, const double* clc, int32_t B, int64_t N,
+                    double* out_sk);
+/* device resident, asynchronous on the context's stream: d_clc dev [B][N] -> d_sk dev [B] */
+int bfl_noise_sigma_dev(bfl_ctx* ctx, const bfl_noise_spec* spec, const double* d_clc, int32_t B, int64_t N,
+                        double* d_sk);
+
 /* ---- OddsRatioDetector.oddsratio (find.py:741-864), fused -----------------------------
  * hypothesis 0 of the plan is the signal; hypotheses 1.. are noise models; noisepoly adds
  * the polynomial-only noise model first, as find.py:774-782 does.  For a batch of B light
  * curves on the same time base:
- *   clc, cle host [B][N] (cle NULL = zeros), sk host [B]
+ *   clc, cle host [B][N] (cle NULL = zeros)
+ *   sk host [B] noise sigma per curve, or NULL to estimate it on device as `noise` describes
+ *   out_sk host [B] or NULL: the sigmas used
  *   [k0, k1)               samples to produce: (0, N) for every sample, (W/2, N - W/2) when the
  *                          caller ignores the edges (find.py:846-851) -- the truncated-window
  *                          samples are then never computed
@@ -116,8 +136,8 @@ int bfl_window_lnB(bfl_ctx* ctx, bfl_plan* plan, int ihyp, const double* clc, co
  *   out_marg host [(nhyp+1)][B][k1-k0] or NULL: marginalised log Bayes factor of each hypothesis
  *                          (index nhyp = polynomial-only), without the sumlogsigma constant  */
 int bfl_detector_odds(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const double* clc, const double* cle,
-                      const double* sk, int32_t B, int64_t N, int64_t k0, int64_t k1, double* out_lnO,
-                      double* out_marg);
+                      const double* sk, const bfl_noise_spec* noise, int32_t B, int64_t N, int64_t k0,
+                      int64_t k1, double* out_lnO, double* out_marg, double* out_sk);
 
 /* Same, device resident and asynchronous on the context's stream.  Supports time chunks:
  * the buffers hold samples [seg0, seg0+seglen) of series of true length N; log odds are

@@ -325,3 +325,38 @@ def test_error_conventions(capsys):
     lnB, bg = plan.window_lnB(0, clc, np.linspace(0.1, 0.2, 300), 1.0, 0.0, want_bg=True)
     assert np.all(lnB[0, 150 - 27:150 + 28] == -np.inf) and np.all(bg[150 - 27:150 + 28] == -np.inf)
     assert np.all(np.isfinite(lnB[0, :150 - 27])) and np.all(np.isfinite(bg[150 + 28:]))
+
+
+@pytest.mark.parametrize("meth", ["powerspectrum", "tailveto"])
+def test_noise_sigma_on_device_vs_reference_and_host(meth):
+    """the noise estimate on the device against the reference's value (golden)
+    and against the host mirror on a batch, including an odd-length curve."""
+    g = load_golden("detector")
+    det = bf.OddsRatioDetector(_lc(g["a_cts"], g["a_clc"]), noiseestmethod=meth)
+    got = det.noise_sigma_batch(g["a_clc"])[0]
+    ref = float(g["ref_a_sk_ps" if meth == "powerspectrum" else "ref_a_sk_tv"])
+    assert abs(got - ref) <= 1e-12 * ref, (got, ref)
+    rng = np.random.default_rng(31)
+    for N in (1639, 4400):
+        ts = np.arange(N) * DT
+        clc = rng.standard_normal((5, N)) * rng.uniform(0.3, 40, (5, 1)) + 3 * np.sin(ts / 2e5)[None, :]
+        clc[2] += orc.flare_model(ts, ts[N // 3], 300., 1500., 5000.)
+        d = bf.OddsRatioDetector(_lc(ts, clc[0]), noiseestmethod=meth, tvsigma=1.3, psestfrac=0.4)
+        dev = d.noise_sigma_batch(clc)
+        host = np.array([d.noise_sigma(_lc(ts, clc[b])) for b in range(5)])
+        np.testing.assert_allclose(dev, host, rtol=1e-12, atol=0)
+
+
+def test_batch_with_device_noise_estimate_vs_oracle():
+    rng = np.random.default_rng(33)
+    B, N = 4, 1200
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal((B, N)) * np.array([[0.7], [1.0], [5.0], [1.7]])
+    clc[1] += orc.flare_model(ts, ts[500], 11., 900., 3000.)
+    for meth in ("powerspectrum", "tailveto"):
+        det = bf.OddsRatioDetector(_lc(ts, clc[0]), noiseestmethod=meth)
+        lnO, sk = det.oddsratio_batch(clc, return_sk=True)
+        for b in range(B):
+            ref, _, _, sk_ref = orc.oddsratio(clc[b], np.zeros(N), ts, noiseestmethod=meth, return_parts=True)
+            assert abs(sk[b] - sk_ref) <= 1e-12 * sk_ref
+            assert_logodds_close(lnO[b], ref, TOL, "device noise %s %d" % (meth, b))
