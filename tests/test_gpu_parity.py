@@ -360,3 +360,64 @@ def test_batch_with_device_noise_estimate_vs_oracle():
             ref, _, _, sk_ref = orc.oddsratio(clc[b], np.zeros(N), ts, noiseestmethod=meth, return_parts=True)
             assert abs(sk[b] - sk_ref) <= 1e-12 * sk_ref
             assert_logodds_close(lnO[b], ref, TOL, "device noise %s %d" % (meth, b))
+
+
+# ---- size-independent properties at BASELINE's full sizes ------------------------------------
+def test_full_size_batch_properties_config3():
+    """1,024 x 4,400 (config 3 on one GPU): (i) every sampled curve of the batch equals its
+    single-curve run to rounding, (ii) permuting curves permutes results, (iii) the oracle on two
+    curves, (iv) strong injected flares are recovered at their injection time."""
+    from bayesflare_b200.synthetic import simulate_batch
+    B, N = 1024, 4400
+    cts, clc, truth = simulate_batch(B, N, seed=7)
+    det = bf.OddsRatioDetector(_lc(cts, clc[0]))
+    lnO, sk = det.oddsratio_batch(clc, return_sk=True)
+    assert lnO.shape == (B, N - 54) and np.all(np.isfinite(lnO))
+    for b in (0, 137, 512, 1023):
+        single = det.plan().detector_odds(clc[b], None, sk[b], k0=27, k1=N - 27)
+        np.testing.assert_allclose(lnO[b], single, rtol=0, atol=5e-13)
+    # permuting the curves of a batch permutes the output rows (no cross-talk between curves)
+    perm = np.random.default_rng(0).permutation(64)
+    again = det.plan().detector_odds(clc[perm], None, sk[perm], k0=27, k1=N - 27)
+    np.testing.assert_allclose(again, lnO[perm], rtol=0, atol=5e-13)
+    for b in (3, 700):
+        ref, _ = orc.oddsratio(clc[b], np.zeros(N), cts, sk=sk[b])
+        assert_logodds_close(lnO[b], ref, TOL, "config3 curve %d" % b)
+        np.testing.assert_array_equal(np.nonzero(lnO[b] > 16.5)[0], np.nonzero(ref > 16.5)[0])
+    # injected flares with SNR > 20 are found at their injection time (+-2 samples)
+    strong = np.nonzero(truth["snr"] > 20)[0][:64]
+    hits = [np.any(lnO[b, truth["idx"][b] - 27 - 2:truth["idx"][b] - 27 + 3] > 16.5) for b in strong]
+    assert np.mean(hits) > 0.95
+
+
+def test_full_size_short_cadence_properties_config2():
+    """130,000-sample series (config 2): a time shift of the data shifts the log odds (translation
+    invariance of the interior path), and 8 halo'd chunks reproduce the whole series."""
+    torch = pytest.importorskip("torch")
+    from bayesflare_b200.parallel import time_chunks
+    rng = np.random.default_rng(2)
+    N = 130000
+    ts = np.arange(N) * 58.84876
+    clc = rng.standard_normal(N)
+    for idx in (20000, 64000, 99000):
+        clc[idx - 100:idx + 600] += 9.0 * orc.flare_model(ts[idx - 100:idx + 600], ts[idx], 1., 250., 900.)
+    det = bf.OddsRatioDetector(_lc(ts, clc))
+    plan, sk = det.plan(), 1.0
+    whole = plan.detector_odds(clc, None, sk, k0=27, k1=N - 27)
+    assert np.all(np.isfinite(whole))
+    shift = 1234
+    rolled = plan.detector_odds(np.roll(clc, shift), None, sk, k0=27, k1=N - 27)
+    np.testing.assert_allclose(rolled[shift + 60:-60], whole[60:-shift - 60], rtol=0, atol=1e-12)
+    dev = torch.device("cuda:0")
+    d_sk = torch.tensor([sk], dtype=torch.float64, device=dev)
+    out = np.empty(N - 54)
+    for k0, k1, s0, s1 in time_chunks(N, 8, 55, True):
+        d_seg = torch.tensor(clc[s0:s1], dtype=torch.float64, device=dev)
+        d_out = torch.empty(k1 - k0, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        plan.detector_odds_dev(d_seg.data_ptr(), 0, True, d_sk.data_ptr(), 1, N, s0, s1 - s0, k0, k1, d_out.data_ptr())
+        plan.ctx.sync()
+        out[k0 - 27:k1 - 27] = d_out.cpu().numpy()
+    np.testing.assert_allclose(out, whole, rtol=0, atol=2e-13)
+    fl, n, mx = det.thresholder(whole, 16.5, expand=1)
+    assert n >= 3 and all(any(abs(m[1] + 27 - idx) <= 3 for m in mx) for idx in (20000, 64000, 99000))

@@ -19,7 +19,7 @@ ctx.set_timing(True); ctx.window_time()
 for it in range(5):
     lnO = plan.detector_odds(clc, None, sk, k0=27, k1=N-27)
 ms, n = ctx.window_time()
-ms /= n
+ms /= 5   # per call (the pipelined host entry launches the kernel once per sub-batch)
 units = B*(N-54)*92
 fl = B*(N-54)*(92*132+575)
 print('KT env', __import__('os').environ.get('BFL_KT'), 'window ms %.3f  units/s %.3e  TF(survey) %.2f  frac %.3f  strict %.3f  peak %.2f' % (ms, units/ms*1e3, fl/ms/1e9, fl/ms/1e9/peak, B*(N-54)*92*110/ms/1e9/peak, peak), 'chk', float(np.nanmax(lnO)))
