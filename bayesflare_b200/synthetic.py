@@ -17,15 +17,17 @@ DT_SHORT = 58.84876        # s
 __all__ = ["DT_LONG", "DT_SHORT", "simulate_batch"]
 
 
-def simulate_batch(B, N, dt=DT_LONG, seed=0, nstd=1.0, sinusoid_amp=0.0, inject=True, snr_range=(0., 50.)):
-    """Return ``(cts[N], clc[B, N], truth)``; curve ``i`` uses ``default_rng(1000*seed + i)``."""
+def simulate_batch(B, N, dt=DT_LONG, seed=0, nstd=1.0, sinusoid_amp=0.0, inject=True, snr_range=(0., 50.), first=0):
+    """Return ``(cts[N], clc[B, N], truth)``.  Curve ``i`` of the batch is realisation ``first + i`` and
+    uses ``default_rng([seed, first + i])``, so a sweep sharded over ranks simulates the same curves
+    whatever the number of ranks."""
     cts = np.arange(N, dtype=np.float64) * dt
     clc = np.empty((B, N))
     truth = {"idx": np.zeros(B, dtype=np.int64), "snr": np.zeros(B), "taugauss": np.zeros(B), "tauexp": np.zeros(B)}
     flare = Flare(cts, amp=1.)
     h = 27
     for i in range(B):
-        rng = np.random.default_rng(1000 * seed + i)
+        rng = np.random.default_rng([int(seed), int(first) + i])
         x = nstd * rng.standard_normal(N)
         if sinusoid_amp > 0:
             amp = rng.uniform(0, sinusoid_amp) * nstd

@@ -421,3 +421,17 @@ def test_full_size_short_cadence_properties_config2():
     np.testing.assert_allclose(out, whole, rtol=0, atol=2e-13)
     fl, n, mx = det.thresholder(whole, 16.5, expand=1)
     assert n >= 3 and all(any(abs(m[1] + 27 - idx) <= 3 for m in mx) for idx in (20000, 64000, 99000))
+
+
+def test_injection_sweep_driver_config5_small():
+    """BASELINE config 5 mechanics on a small sweep: counters are consistent, strong flares are found,
+    and sharding the realisations differently (as 1 or 3 ranks would) gives the same counters."""
+    from bayesflare_b200.sweep import detection_efficiency
+    whole = detection_efficiency(600, N=1639, seed=4, batch=256)
+    assert whole["injected"].sum() == 600 and np.all(whole["detected"] <= whole["injected"])
+    assert whole["detected"][25:].sum() >= 0.97 * whole["injected"][25:].sum()
+    assert whole["detected"][:3].sum() <= 0.2 * max(whole["injected"][:3].sum(), 1)
+    parts = [detection_efficiency(600, N=1639, seed=4, batch=256, rank=r, world=3) for r in range(3)]
+    np.testing.assert_array_equal(sum(p["injected"] for p in parts), whole["injected"])
+    np.testing.assert_array_equal(sum(p["detected"] for p in parts), whole["detected"])
+    assert sum(p["false_alarms"] for p in parts) == whole["false_alarms"]
