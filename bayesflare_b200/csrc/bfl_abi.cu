@@ -393,9 +393,19 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   const int nnoise = pv.nhyp - 1 + (noisepoly ? 1 : 0);
   const bool need_bg = (d_marg != nullptr) || nnoise == 0;
   Scratch sc{};
-  if ((rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc))) return rc;
+  // first pass without the partial-sum buffer: it is not needed when the kernel can fuse the combine
+  if ((rc = setup_scratch(c, pv, sv, need_general, need_bg, false, sc))) return rc;
+  const bool fused = sv.const_var && !edges && !need_bg && fast_can_fuse(pv, sc, noisepoly);
+  if (!fused && (rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc))) return rc;
   cudaStream_t s = c->stream;
   CK(launch_prep(sv, sc, need_general, s, &c->stats));
+  if (fused) {
+    std::pair<cudaEvent_t, cudaEvent_t> pr;
+    if (c->timing && (rc = timing_begin(c, pr))) return rc;
+    CK(launch_window_fast_fused(pv, sv, sc, noisepoly, d_lnO, s, &c->stats));
+    if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
+    return BFL_OK;
+  }
   if (sv.const_var) {
     std::pair<cudaEvent_t, cudaEvent_t> pr;
     if (c->timing && (rc = timing_begin(c, pr))) return rc;

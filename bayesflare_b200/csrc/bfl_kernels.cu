@@ -312,6 +312,8 @@ struct FastArgs {
   const double* bgabs;    // FULL mode: [nk]
   double sls;             // FULL mode: sumlogsigma
   int ihyp;               // FULL mode
+  double* lnO;            // FUSED mode (MODE 2): log odds written directly, [B][nk]
+  int noisepoly;          // FUSED mode
 };
 
 constexpr int FAST_TPB = 128;
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
     for (int i = tid; i < WP; i += FAST_TPB) stmpl[(size_t)(ge - gb) * WP + i] = 0.0;   // pipeline pad row
     for (int i = tid; i < ge - gb; i += FAST_TPB) {
       double k = a.Kg[gb + i] + a.lp[gb + i];
-      if (MODE == 0) k += a.lw[gb + i];
+      if (MODE != 1) k += a.lw[gb + i];
       sK[i] = k;
     }
     if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
@@ -466,13 +468,37 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
 #pragma unroll
   for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
 
+  // MODE 2 (fused): the hypotheses are combined in registers, find.py:853-862 -- numerator = the
+  // signal's marginal, denominator = sum over [polynomial-only (= 1 in these units), noise models].
+  // Both are kept as (max, sum) pairs and merged with one cheap exp per hypothesis; a single log per
+  // sample is taken at the end.  Needs every template of the plan in this CTA's chunk (NC == 1).
+  double n_m[KT], n_s[KT], d_m[KT], d_s[KT];
+#pragma unroll
+  for (int j = 0; j < KT; j++) {
+    n_m[j] = LSE_EMPTY; n_s[j] = 0.0;
+    d_m[j] = a.noisepoly ? 0.0 : LSE_EMPTY; d_s[j] = a.noisepoly ? 1.0 : 0.0;
+  }
   auto flush = [&](int hh) {
+    const double hc = (a.hyp_half[hh] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
     if (MODE == 0) {
-      const double hc = (a.hyp_half[hh] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
       double2* p = a.part + ((size_t)(hh * a.NC + chunk) * a.B + b) * nk;
 #pragma unroll
       for (int j = 0; j < KT; j++) {
         if (valid[j]) p[kfirst + j - a.k0] = make_double2(mx[j] + hc, sm[j]);
+        mx[j] = LSE_EMPTY; sm[j] = 0.0;
+      }
+    } else if (MODE == 2) {
+#pragma unroll
+      for (int j = 0; j < KT; j++) {
+        const double x = mx[j] + hc;
+        if (hh == 0) { n_m[j] = x; n_s[j] = sm[j]; }
+        else {
+          const double d = x - d_m[j];
+          const double e = exp_nonpos(-fabs(d), st64);
+          const bool up = d > 0.0;
+          d_s[j] = up ? fma(d_s[j], e, sm[j]) : fma(sm[j], e, d_s[j]);
+          d_m[j] = up ? x : d_m[j];
+        }
         mx[j] = LSE_EMPTY; sm[j] = 0.0;
       }
     }
@@ -515,7 +541,7 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
       for (int j = 0; j < KT; j++)
         if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
     }
-    if (MODE == 0) {
+    if (MODE != 1) {
 #pragma unroll
       for (int j = 0; j < KT; j++) lse_push(mx[j], sm[j], val[j], st64);
     } else {
@@ -534,6 +560,12 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
 #endif
   }
   flush(h);
+  if (MODE == 2) {
+    double* o = a.lnO + (size_t)b * nk;
+#pragma unroll
+    for (int j = 0; j < KT; j++)
+      if (valid[j]) o[kfirst + j - a.k0] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
+  }
   }   // warp-tile loop
 }
 
@@ -821,7 +853,7 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   for (int h = 0; h < pv.nhyp; h++) a.hyp_half[h] = pv.hyp_half[h];
   a.part = sc.part;
-  a.out_full = nullptr; a.bgabs = sc.bgabs; a.sls = 0.0; a.ihyp = 0;
+  a.out_full = nullptr; a.bgabs = sc.bgabs; a.sls = 0.0; a.ihyp = 0; a.lnO = nullptr; a.noisepoly = 0;
 }
 
 template <int MODE>
@@ -887,6 +919,22 @@ cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scr
   fill_fast_args(a, pv, sv, sc, KT);
   if (use_ws(a, KT)) return launch_ws_impl<0>(a, s, st);
   return launch_fast_impl<0>(a, KT, s, st);
+}
+
+// fused detector: log odds straight from the window kernel (no partials, no combine launch).
+// Valid when every template sits in one chunk, there is at least one noise model, and the sample
+// range holds no truncated windows.
+bool fast_can_fuse(const PlanView& pv, const Scratch& sc, int noisepoly) {
+  return sc.NC == 1 && sc.sub == 1 && (pv.nhyp - 1 + (noisepoly ? 1 : 0)) > 0 && pv.G > 0 && pv.hyp_begin[1] > 0;
+}
+
+cudaError_t launch_window_fast_fused(const PlanView& pv, const SeriesView& sv, Scratch& sc, int noisepoly,
+                                     double* d_lnO, cudaStream_t s, LaunchStats* st) {
+  FastArgs a;
+  const int KT = kt_for(pv, sv, sc);
+  fill_fast_args(a, pv, sv, sc, KT);
+  a.lnO = d_lnO; a.noisepoly = noisepoly;
+  return launch_fast_impl<2>(a, KT, s, st);
 }
 
 cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,

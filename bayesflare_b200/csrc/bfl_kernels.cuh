@@ -73,6 +73,9 @@ cudaError_t launch_bgproj(const PlanView& pv, const SeriesView& sv, Scratch& sc,
 // fused window kernel, log-sum-exp mode (detector) -- interior, constant variance
 cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
                                    LaunchStats* st);
+bool fast_can_fuse(const PlanView& pv, const Scratch& sc, int noisepoly);
+cudaError_t launch_window_fast_fused(const PlanView& pv, const SeriesView& sv, Scratch& sc, int noisepoly,
+                                     double* d_lnO, cudaStream_t s, LaunchStats* st);
 // fused window kernel, full output mode for one hypothesis: out[gorig][B? no: single curve][nk]
 cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
                                     double sumlogsigma, double* d_out, cudaStream_t s, LaunchStats* st);

@@ -320,9 +320,16 @@ def run_ours(args, rank, local_rank, world):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    alg_bytes = float(B) * N * 8.0 + float(B) * NK * 16.0 * len(models)   # read data, write partials
+    alg_bytes = float(B) * N * 8.0 + float(B) * NK * 8.0   # read the light curves, write the log odds
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_window_traffic_r1.json")))
+        if B == 1024 and N == 4400:
+            traffic = tj["traffic_bytes_per_launch"]      # dram read + write of one launch, ncu --set full
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "kernel": "k_window_fast<55,4,LSE>", "kernel_ms": win_avg_ms,
+                "traffic": traffic, "kernel": "k_window_fast<55,4,FUSED>", "kernel_ms": win_avg_ms,
                 "kernel_share_of_step": win_ms / ms_total,
                 "peak_source": "measured live by bfl_fp64_peak_probe (16 independent DFMA chains/thread, burst); "
                                "FP64 is not in MEASURED_PEAKS.json",
