@@ -108,7 +108,7 @@ __device__ __forceinline__ double exp_nonpos(double d, const double* __restrict_
 __device__ __forceinline__ void lse_push(double& m, double& s, double x, const double* __restrict__ t64) {
   const double d = x - m;
   const double e = exp_nonpos(-fabs(d), t64);
-  const bool up = d > 0.0;
+  const bool up = __double2hiint(d) >= 0;     // sign bit (integer pipe); d == 0 gives the same sum either way
   s = fma(s, up ? e : 1.0, up ? 1.0 : e);
   m = up ? x : m;
 }
