@@ -73,6 +73,7 @@ SIGNATURES = {
                                   C.POINTER(C.c_void_p)]),
     "bfl_plan_destroy": (C.c_int, [C.c_void_p]),
     "bfl_plan_templates": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "bfl_plan_shape_count": (C.c_int, [C.c_void_p]),
     "bfl_window_lnB": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.c_double, C.c_int64, C.c_double,
                                  _dp, _dp]),
     "bfl_noise_sigma": (C.c_int, [C.c_void_p, C.POINTER(NoiseSpec), _dp, C.c_int32, C.c_int64, _dp]),
@@ -213,6 +214,11 @@ class Plan:
         check(self.lib.bfl_plan_create(ctx.handle, self.bglen, self.npoly, ptr(bg), ptr(keep[1]), arr, self.nhyp,
                                        C.byref(hnd)))
         self.handle = hnd
+
+    @property
+    def shape_count(self):
+        """Correlation shapes per sample in the separable form, or -1 (dense form only)."""
+        return int(self.lib.bfl_plan_shape_count(self.handle))
 
     def templates(self, ihyp):
         out = np.zeros((self.ngrid[ihyp], self.bglen))

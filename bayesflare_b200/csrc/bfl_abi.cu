@@ -273,6 +273,58 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
   }
   pv.logdetG = (double)logdet;
 
+  // ---- separable-grid form ------------------------------------------------------------------
+  // A Flare template is rise(tau_gauss) (+) centre sample (+) decay(tau_exp) on disjoint supports, so
+  // m(tg, te) = m(tg, 0) + m(0, te) - m(0, 0) exactly, and the same holds after the (linear) projection
+  // off the background basis.  For a grid of nA x nB time scales only nA + nB + 1 correlations per
+  // sample are needed instead of nA * nB: shapes A_i = m_perp(tg_i, 0) - m_perp(0, 0), B_j = m_perp(0, te_j),
+  // z_g = (A_i . d + B_j . d) / |m_perp_g|.  Other hypotheses stay dense (one shape per template).
+  std::vector<TemplDesc> sdesc;            // shapes that must be generated (separable hypotheses)
+  std::vector<int> sdesc_at;               // their row in the shape table
+  std::vector<int> dense_src, dense_at;    // dense templates: row of `hat` -> row in the shape table
+  std::vector<short> idxA(G, -1), idxB(G, 0);
+  struct SubC { int a0, na, c; };
+  std::vector<SubC> sub_c;                 // per separable hypothesis: first A row, number of A rows, C row
+  int S = 0;
+  bool sep_ok = (W == 55);
+  for (int h = 0; h < nhyp && sep_ok; h++) {
+    const int g0 = pv.hyp_begin[h], g1 = pv.hyp_begin[h + 1];
+    pv.hyp_A0[h] = 0; pv.hyp_nA[h] = 0;
+    bool sep = hyps[h].kind == BFL_MODEL_FLARE && g1 - g0 >= 4;
+    std::vector<double> tgs, tes;
+    if (sep) {
+      for (int g = g0; g < g1 && sep; g++) {
+        if (desc[g].p[0] != desc[g0].p[0] || desc[g].p[3] != desc[g0].p[3]) sep = false;   // one t0, one amp
+        if (std::find(tgs.begin(), tgs.end(), desc[g].p[2]) == tgs.end()) tgs.push_back(desc[g].p[2]);
+        if (std::find(tes.begin(), tes.end(), desc[g].p[1]) == tes.end()) tes.push_back(desc[g].p[1]);
+      }
+      if ((int)tgs.size() > 1024 || (int)(tgs.size() + tes.size() + 1) >= g1 - g0) sep = false;
+    }
+    if (sep) {
+      const int A0 = S, B0 = S + (int)tgs.size(), C = B0 + (int)tes.size();
+      pv.hyp_A0[h] = A0; pv.hyp_nA[h] = (int)tgs.size();
+      for (size_t i = 0; i < tgs.size(); i++) {
+        TemplDesc d = desc[g0]; d.p[1] = 0.0; d.p[2] = tgs[i];
+        sdesc.push_back(d); sdesc_at.push_back(A0 + (int)i);
+      }
+      for (size_t j = 0; j < tes.size(); j++) {
+        TemplDesc d = desc[g0]; d.p[1] = tes[j]; d.p[2] = 0.0;
+        sdesc.push_back(d); sdesc_at.push_back(B0 + (int)j);
+      }
+      { TemplDesc d = desc[g0]; d.p[1] = 0.0; d.p[2] = 0.0; sdesc.push_back(d); sdesc_at.push_back(C); }
+      for (int g = g0; g < g1; g++) {
+        idxA[g] = (short)(std::find(tgs.begin(), tgs.end(), desc[g].p[2]) - tgs.begin());
+        idxB[g] = (short)(B0 + (std::find(tes.begin(), tes.end(), desc[g].p[1]) - tes.begin()));
+      }
+      sub_c.push_back({A0, (int)tgs.size(), C});
+      S = C + 1;
+    } else {
+      for (int g = g0; g < g1; g++) { dense_src.push_back(g); dense_at.push_back(S); idxB[g] = (short)S; S++; }
+    }
+    if (S > 30000) sep_ok = false;
+  }
+  pv.S = S;
+
   void *d_desc, *d_mts, *d_raw, *d_hat, *d_Kg, *d_lp, *d_lw, *d_gorig, *d_bg, *d_bb, *d_qb;
   int rc;
 #define PA(ptr, bytes) if ((rc = plan_alloc(p, (bytes), &(ptr))) != BFL_OK) { bfl_plan_destroy(p); return rc; }
@@ -306,16 +358,47 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
   for (size_t i = 0; i < table_at.size(); i++)
     CKP(cudaMemcpyAsync((double*)d_raw + (size_t)table_at[i] * WP, table_rows.data() + i * W, sizeof(double) * (size_t)W,
                         cudaMemcpyHostToDevice, s));
+  void *d_inorm = nullptr, *d_shapes = nullptr, *d_idxA = nullptr, *d_idxB = nullptr;
+  if ((rc = plan_alloc(p, sizeof(double) * (size_t)std::max(G, 1), &d_inorm))) { bfl_plan_destroy(p); return rc; }
   CKP(launch_plan_orthonormalise((const double*)d_raw, (const double*)d_qb, G, W, WP, P, (double*)d_hat,
-                                 (double*)d_Kg, s, &c->stats));
+                                 (double*)d_Kg, (double*)d_inorm, 1, s, &c->stats));
+  if (sep_ok && G > 0) {
+    void *d_sdesc, *d_sraw, *d_sperp;
+    const int ns = (int)sdesc.size();
+    if ((rc = plan_alloc(p, sizeof(double) * (size_t)S * WP, &d_shapes)) ||
+        (rc = plan_alloc(p, sizeof(short) * (size_t)G, &d_idxA)) || (rc = plan_alloc(p, sizeof(short) * (size_t)G, &d_idxB)) ||
+        (rc = plan_alloc(p, sizeof(TemplDesc) * (size_t)std::max(ns, 1), &d_sdesc)) ||
+        (rc = plan_alloc(p, sizeof(double) * (size_t)std::max(ns, 1) * WP, &d_sraw)) ||
+        (rc = plan_alloc(p, sizeof(double) * (size_t)std::max(ns, 1) * WP, &d_sperp))) { bfl_plan_destroy(p); return rc; }
+    CKP(cudaMemcpyAsync(d_idxA, idxA.data(), sizeof(short) * (size_t)G, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_idxB, idxB.data(), sizeof(short) * (size_t)G, cudaMemcpyHostToDevice, s));
+    if (ns > 0) {
+      CKP(cudaMemcpyAsync(d_sdesc, sdesc.data(), sizeof(TemplDesc) * (size_t)ns, cudaMemcpyHostToDevice, s));
+      CKP(launch_gen_templates((const TemplDesc*)d_sdesc, ns, (const double*)d_mts, W, WP, (double*)d_sraw, s, &c->stats));
+      CKP(launch_plan_orthonormalise((const double*)d_sraw, (const double*)d_qb, ns, W, WP, P, (double*)d_sperp, nullptr,
+                                     nullptr, 0, s, &c->stats));
+      for (int i = 0; i < ns; i++)
+        CKP(cudaMemcpyAsync((double*)d_shapes + (size_t)sdesc_at[i] * WP, (double*)d_sperp + (size_t)i * WP,
+                            sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
+      for (auto& ac : sub_c) CKP(launch_subtract_row((double*)d_shapes, ac.a0, ac.na, ac.c, WP, s, &c->stats));
+    }
+    for (size_t i = 0; i < dense_src.size(); i++)
+      CKP(cudaMemcpyAsync((double*)d_shapes + (size_t)dense_at[i] * WP, (double*)d_hat + (size_t)dense_src[i] * WP,
+                          sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
+  }
   CKP(cudaStreamSynchronize(s));   // host vectors above go out of scope
 #undef CKP
+  pv.sep_ok = (sep_ok && G > 0) ? 1 : 0;
+  pv.shapes = (const double*)d_shapes; pv.inorm = (const double*)d_inorm;
+  pv.idxA = (const short*)d_idxA; pv.idxB = (const short*)d_idxB;
   pv.raw = (const double*)d_raw; pv.hat = (const double*)d_hat; pv.Kg = (const double*)d_Kg;
   pv.lp = (const double*)d_lp; pv.lw = (const double*)d_lw; pv.gorig = (const int*)d_gorig;
   pv.bg = (const double*)d_bg; pv.bb = (const double*)d_bb; pv.qb = (const double*)d_qb;
   *out = p;
   return BFL_OK;
 }
+
+int bfl_plan_shape_count(const bfl_plan* p) { return (p && p->pv.sep_ok) ? p->pv.S : -1; }
 
 int bfl_plan_templates(bfl_plan* p, int ihyp, double* out) {
   if (!p || !out || ihyp < 0 || ihyp >= p->pv.nhyp) return fail(BFL_ERR_ARG, "bad argument to bfl_plan_templates");
@@ -340,9 +423,13 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   const int64_t nk = sv.k1 - sv.k0;
   int KT = 1;
   sc.gchunk = pick_gchunk(std::max(pv.G, 1), pv.W, (int64_t)sv.B * nk, c->sm_count, &KT);
+  // separable form: whole plan in one CTA -- only when there are enough warp tiles to fill the chip;
+  // small problems keep the template-chunked dense form, which spreads one curve over all SMs
+  if (sv.const_var && fast_sep_fits(pv, KT) && (int64_t)sv.B * nk >= (int64_t)32 * KT * 2 * c->sm_count)
+    sc.gchunk = std::max(pv.G, 1);
   sc.KT = KT;
   sc.NC = (std::max(pv.G, 1) + sc.gchunk - 1) / sc.gchunk;
-  sc.sub = (sv.const_var && fast_uses_ws(pv.W, KT, sc.gchunk)) ? 2 : 1;
+  sc.sub = 1;
   int rc;
   void* ptr;
   if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;

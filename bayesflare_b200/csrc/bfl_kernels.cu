@@ -205,9 +205,11 @@ __global__ void k_gen_templates(const TemplDesc* __restrict__ desc, int G, const
 }
 
 // One thread per template: remove the projection on the orthonormal background basis
-// (twice, for orthogonality at rounding level), normalise, record -0.5 log|m_perp|^2.
+// (twice, for orthogonality at rounding level); optionally normalise; record
+// -0.5 log|m_perp|^2 and 1/|m_perp|.
 __global__ void k_plan_orthonormalise(const double* __restrict__ raw, const double* __restrict__ qb, int G,
-                                      int W, int WP, int P, double* __restrict__ hat, double* __restrict__ Kg) {
+                                      int W, int WP, int P, double* __restrict__ hat, double* __restrict__ Kg,
+                                      double* __restrict__ inorm, int normalise) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   double* h = hat + (size_t)g * WP;
@@ -224,8 +226,17 @@ __global__ void k_plan_orthonormalise(const double* __restrict__ raw, const doub
   double X = 0.0;
   for (int w = 0; w < W; w++) X = fma(h[w], h[w], X);
   const double inv = 1.0 / sqrt(X);
-  for (int w = 0; w < W; w++) h[w] *= inv;
-  Kg[g] = -0.5 * log(X);
+  if (normalise)
+    for (int w = 0; w < W; w++) h[w] *= inv;
+  if (Kg) Kg[g] = -0.5 * log(X);
+  if (inorm) inorm[g] = inv;
+}
+
+__global__ void k_subtract_row(double* rows, int a0, int nA, int c, int WP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nA * WP) return;
+  const int r = i / WP, w = i - r * WP;
+  rows[(size_t)(a0 + r) * WP + w] -= rows[(size_t)c * WP + w];
 }
 
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
@@ -238,9 +249,17 @@ cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d
 }
 
 cudaError_t launch_plan_orthonormalise(const double* d_raw, const double* d_qb, int G, int W, int WP, int P,
-                                       double* d_hat, double* d_Kg, cudaStream_t s, LaunchStats* st) {
+                                       double* d_hat, double* d_Kg, double* d_inorm, int normalise, cudaStream_t s,
+                                       LaunchStats* st) {
   if (G == 0) return cudaSuccess;
-  k_plan_orthonormalise<<<(G + 63) / 64, 64, 0, s>>>(d_raw, d_qb, G, W, WP, P, d_hat, d_Kg);
+  k_plan_orthonormalise<<<(G + 63) / 64, 64, 0, s>>>(d_raw, d_qb, G, W, WP, P, d_hat, d_Kg, d_inorm, normalise);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_subtract_row(double* d_rows, int a0, int nA, int c, int WP, cudaStream_t s, LaunchStats* st) {
+  if (nA <= 0) return cudaSuccess;
+  k_subtract_row<<<(nA * WP + 127) / 128, 128, 0, s>>>(d_rows, a0, nA, c, WP);
   st->launches++;
   return cudaGetLastError();
 }
@@ -314,6 +333,11 @@ struct FastArgs {
   int ihyp;               // FULL mode
   double* lnO;            // FUSED mode (MODE 2): log odds written directly, [B][nk]
   int noisepoly;          // FUSED mode
+  // separable-grid form (SEP kernels)
+  const double* shapes; const double* inorm; const short* idxA; const short* idxB;
+  int S;
+  int hyp_A0[MAXH];
+  int hyp_nA[MAXH];
 };
 
 constexpr int FAST_TPB = 128;
@@ -344,9 +368,6 @@ __device__ __forceinline__ void correlate_reg(const double* __restrict__ t, cons
 
 // WT > 0: compile-time window length with the data window in registers;
 // WT == 0: run-time window length (any odd W <= MAXW), data window read from shared memory, KT = 1.
-#ifndef BFL_PIPE
-#define BFL_PIPE 0
-#endif
 #ifndef BFL_MINBLOCKS
 #define BFL_MINBLOCKS 2
 #endif
@@ -355,7 +376,10 @@ __device__ __forceinline__ void correlate_reg(const double* __restrict__ t, cons
 // "warp tiles" (32*KT consecutive samples of one light curve) independently of each other --
 // each warp stages its own data window (+ halo) into a private shared-memory slice, so the tile
 // loop contains no block-level barrier.
-template <int WT, int KT, int MODE>
+// SEP: the plan's separable-grid form (PlanView::shapes): per hypothesis the A-shape correlations are
+// computed once per tile into a per-thread shared-memory slice, then every template costs one B-shape
+// correlation per distinct B (amortised over the templates that share it) plus z = inorm * (yA + yB).
+template <int WT, int KT, int MODE, bool SEP>
 __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const FastArgs a) {
   extern __shared__ double smem[];
   const int W = (WT > 0) ? WT : a.W;
@@ -368,23 +392,33 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   const int ge = min(a.G, gb + a.gchunk);
   const int wstride = (TKW + 2 * H + 2) & ~1;    // doubles per warp slice
 
+  const int nrows = SEP ? a.S : a.gchunk;                // shape rows (SEP) or template rows staged
   double* sdata = smem;                                  // [WPB][wstride]
-  double* stmpl = smem + (FAST_TPB / 32) * wstride;      // [gchunk + 1][WP] (last row: zeros)
-  double* sK = stmpl + (size_t)(a.gchunk + 1) * WP;      // [gchunk]  Kg + lp (+ lw)
+  double* stmpl = smem + (FAST_TPB / 32) * wstride;      // [nrows + 1][WP] (last row: zeros)
+  double* sK = stmpl + (size_t)(nrows + 1) * WP;         // [gchunk]  Kg + lp (+ lw)
   double* sphi = sK + ((a.gchunk + 1) & ~1);             // [2][(DEG+1) * NI] phi(z) and z^2/2 tables
   double* st64 = sphi + 2 * BFL_PHI_STRIDE;              // [64] 2^(j/64)
+  double* sInorm = st64 + 64;                            // SEP: [gchunk] 1/|m_perp|
+  short* sIdx = reinterpret_cast<short*>(sInorm + (SEP ? ((a.gchunk + 1) & ~1) : 0));   // SEP: [gchunk][2] (A, B)
+  double* ysm = reinterpret_cast<double*>(sIdx + (SEP ? ((2 * a.gchunk + 7) & ~7) : 0)); // SEP: [SEP_MAXA][KT][FAST_TPB]
 
   // ---- once per CTA: templates of this chunk (16-byte copies) and the function tables ----
   {
-    const double2* src = reinterpret_cast<const double2*>(a.hat + (size_t)gb * WP);
+    const double2* src = reinterpret_cast<const double2*>(SEP ? a.shapes : a.hat + (size_t)gb * WP);
     double2* dst = reinterpret_cast<double2*>(stmpl);
-    const int n2 = (ge - gb) * WP / 2;
+    const int nr = SEP ? a.S : (ge - gb);
+    const int n2 = nr * WP / 2;
     for (int i = tid; i < n2; i += FAST_TPB) dst[i] = __ldg(src + i);
-    for (int i = tid; i < WP; i += FAST_TPB) stmpl[(size_t)(ge - gb) * WP + i] = 0.0;   // pipeline pad row
+    for (int i = tid; i < WP; i += FAST_TPB) stmpl[(size_t)nr * WP + i] = 0.0;   // zero row
     for (int i = tid; i < ge - gb; i += FAST_TPB) {
       double k = a.Kg[gb + i] + a.lp[gb + i];
       if (MODE != 1) k += a.lw[gb + i];
       sK[i] = k;
+      if (SEP) {
+        sInorm[i] = a.inorm[gb + i];
+        sIdx[2 * i] = a.idxA[gb + i];
+        sIdx[2 * i + 1] = a.idxB[gb + i];
+      }
     }
     if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
     for (int i = tid; i < BFL_PHI_STRIDE; i += FAST_TPB) {
@@ -504,247 +538,47 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
     }
   };
 
-  // software pipeline: the correlation for template g+1 is issued in the same straight-line block
-  // as the (latency-bound) epilogue of template g; row (ge - gb) of stmpl is a zero pad row.
+  // hypotheses -> (SEP: passes over groups of A shapes) -> templates
+  double yB[KT];
   double zc[KT];
-#if BFL_PIPE
-  correlate(g0 - gb, zc);
-#endif
-  for (int g = g0; g < g1; g++) {
-#if BFL_PIPE
-    double zn[KT];
-    correlate(g + 1 - gb, zn);
-#elif defined(BFL_EXP_EPI_ONLY)
+  int h_last = h0;
+  while (a.hyp_begin[h_last + 1] < g1) h_last++;
+  for (h = h0; h <= h_last; h++) {
+    const int glo = max(g0, a.hyp_begin[h]), ghi = min(g1, a.hyp_begin[h + 1]);
+    if (glo >= ghi) continue;
+    const int nA = SEP ? a.hyp_nA[h] : 0;
+    const int npass = (nA + SEP_MAXA - 1) / SEP_MAXA > 1 ? (nA + SEP_MAXA - 1) / SEP_MAXA : 1;
+    for (int pass = 0; pass < npass; pass++) {
+      const int ia0 = pass * SEP_MAXA, ia1 = min(nA, ia0 + SEP_MAXA);
+      if constexpr (SEP) {
+        // correlations with this group's A shapes, kept per thread in shared memory
+        for (int ia = ia0; ia < ia1; ia++) {
+          double y[KT];
+          correlate(a.hyp_A0[h] + ia, y);
 #pragma unroll
-    for (int j = 0; j < KT; j++) zc[j] = (BFL_EPI_UNIFORM ? 0.0 : win[j] * 0.9 + win[j + 1] * 0.3) + 0.05 * (g - gb) - 2.0 + 1e-30 * win[j];
-#else
-    correlate(g - gb, zc);
-#endif
-    while (g >= a.hyp_begin[h + 1]) { flush(h); h++; }
-    const bool half = a.hyp_half[h] != 0;
-    const double* tab = sphi + (half ? 0 : BFL_PHI_STRIDE);
-    const double kg = sK[g - gb];
-    double val[KT];
-    bool far_ = false;
-#if defined(BFL_EXP_CORR_ONLY)
-#pragma unroll
-    for (int j = 0; j < KT; j++) { mx[j] += zc[j]; }
-    continue;
-#endif
-#pragma unroll
-    for (int j = 0; j < KT; j++) {
-      val[j] = kg + phi_tab(zc[j], tab);
-      far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
-    }
-    if (half && far_) {   // rare: a > 12 sigma negative amplitude
-#pragma unroll
-      for (int j = 0; j < KT; j++)
-        if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
-    }
-    if (MODE != 1) {
-#pragma unroll
-      for (int j = 0; j < KT; j++) lse_push(mx[j], sm[j], val[j], st64);
-    } else {
-      const double hc = (half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
-#pragma unroll
-      for (int j = 0; j < KT; j++) {
-        if (valid[j]) {
-          const int64_t ki = kfirst + j - a.k0;
-          a.out_full[(size_t)a.gorig[g] * nk + ki] = (val[j] + hc) + (a.bgabs[(size_t)b * nk + ki] + a.sls);
+          for (int j = 0; j < KT; j++) ysm[((ia - ia0) * KT + j) * FAST_TPB + tid] = y[j];
         }
       }
-    }
-#if BFL_PIPE
+      int curB = -1;
+      for (int g = glo; g < ghi; g++) {
+        if constexpr (SEP) {
+          const int ia = sIdx[2 * (g - gb)], ib = sIdx[2 * (g - gb) + 1];
+          if (nA > 0 && (ia < ia0 || ia >= ia1)) continue;         // another pass owns this template
+          if (ib != curB) { curB = ib; correlate(ib, yB); }        // shared by every template with this B shape
+          if (ia >= 0) {
+            const double sc = sInorm[g - gb];
 #pragma unroll
-    for (int j = 0; j < KT; j++) zc[j] = zn[j];
-#endif
-  }
-  flush(h);
-  if (MODE == 2) {
-    double* o = a.lnO + (size_t)b * nk;
+            for (int j = 0; j < KT; j++) zc[j] = sc * (ysm[((ia - ia0) * KT + j) * FAST_TPB + tid] + yB[j]);
+          } else {
 #pragma unroll
-    for (int j = 0; j < KT; j++)
-      if (valid[j]) o[kfirst + j - a.k0] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
-  }
-  }   // warp-tile loop
-}
-
-// ======================================================================================
-// FAST path, warp-specialised variant (W = 55, large batches)
-// ======================================================================================
-// One persistent CTA per SM: 4 PRODUCER warps (one per SM sub-partition) hold the register
-// data window and do nothing but the correlation z = m_hat . d for template after template;
-// 8 CONSUMER warps (two per producer) take z through a shared-memory ring and run the
-// latency/LSU-bound part: phi(z) table look-up, log-sum-exp.  Producers keep the FP64 pipe fed
-// while consumers wait on shared-memory latency, which an in-order warp doing both cannot.
-// Ring slots are handed over with mbarriers (full / empty, one arrival each).
-constexpr int WS_D = 8;            // ring depth in templates
-constexpr int WS_NP = 4;           // producer warps
-constexpr int WS_NC = 2;           // consumers per producer
-constexpr int WS_THREADS = 32 * WS_NP * (1 + WS_NC);
-constexpr int WS_W = 55, WS_KT = 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      "WAIT_%=:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      " @p bra DONE_%=;\n"
-      " bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(WS_THREADS, 1) k_window_ws(const FastArgs a) {
-  extern __shared__ double smem[];
-  constexpr int W = WS_W, H = W / 2, KT = WS_KT, TKW = 32 * KT;
-  const int WP = a.WP;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk = blockIdx.y;
-  const int gb = chunk * a.gchunk;
-  const int ge = min(a.G, gb + a.gchunk);
-  constexpr int wstride = (TKW + 2 * H + 2) & ~1;
-
-  double* swinall = smem;                                    // [WS_NP][wstride]
-  double* zring = swinall + WS_NP * wstride;                 // [WS_NP][WS_D][KT][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(zring + WS_NP * WS_D * KT * 32);   // full[NP][D], empty[NP][D]
-  double* stmpl = reinterpret_cast<double*>(bars + 2 * WS_NP * WS_D);             // [gchunk][WP]
-  double* sK = stmpl + (size_t)a.gchunk * WP;                // [gchunk]
-  double* sphi = sK + ((a.gchunk + 1) & ~1);                 // [2][(DEG+1)*NI]
-  double* st64 = sphi + 2 * BFL_PHI_STRIDE;                  // [64]
-
-  {
-    const double2* src = reinterpret_cast<const double2*>(a.hat + (size_t)gb * WP);
-    double2* dst = reinterpret_cast<double2*>(stmpl);
-    const int n2 = (ge - gb) * WP / 2;
-    for (int i = tid; i < n2; i += WS_THREADS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < ge - gb; i += WS_THREADS) {
-      double k = a.Kg[gb + i] + a.lp[gb + i];
-      if (MODE == 0) k += a.lw[gb + i];
-      sK[i] = k;
-    }
-    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
-    for (int i = tid; i < BFL_PHI_STRIDE; i += WS_THREADS) {
-      sphi[i] = BFL_PHI_TAB[i];
-      const int c = i / BFL_PHI_NI, kk = i - c * BFL_PHI_NI;
-      const double zk = BFL_PHI_ZMIN + kk * (1.0 / BFL_PHI_INVH), hh = 1.0 / BFL_PHI_INVH;
-      sphi[BFL_PHI_STRIDE + i] = (c == 0) ? 0.5 * zk * zk : (c == 1) ? zk * hh : (c == 2) ? 0.5 * hh * hh : 0.0;
-    }
-    if (tid < WS_NP * WS_D) {
-      mbar_init(bars + tid, 1);                        // full: the producer's lane 0
-      mbar_init(bars + WS_NP * WS_D + tid, 1);         // empty: lane 0 of the consumer that owns the template
-    }
-  }
-  __syncthreads();
-
-  int g0 = gb, g1 = ge;
-  if (MODE == 1) { g0 = max(gb, a.hyp_begin[a.ihyp]); g1 = min(ge, a.hyp_begin[a.ihyp + 1]); }
-  if (g0 >= g1) return;
-  const int64_t nk = a.k1 - a.k0;
-  const bool producer = warp < WS_NP;
-  const int p = producer ? warp : (warp - WS_NP) % WS_NP;     // ring id == SM sub-partition
-  const int c = producer ? 0 : (warp - WS_NP) / WS_NP;        // consumer index within the ring
-  uint64_t* full = bars + p * WS_D;
-  uint64_t* empty = bars + WS_NP * WS_D + p * WS_D;
-  double* ring = zring + (size_t)p * WS_D * KT * 32;
-  uint32_t step = 0;                                           // templates handed over so far
-
-  for (int64_t wt = (int64_t)blockIdx.x * WS_NP + p; wt < a.total_wtiles; wt += (int64_t)gridDim.x * WS_NP) {
-    const int tile = (int)(wt % a.tiles_per_curve);
-    const int b = (int)(wt / a.tiles_per_curve);
-    const int64_t kbase = a.k0 + (int64_t)tile * TKW;
-
-    if (producer) {
-      // ---- stage this warp's slice + halo, then keep the window in registers ----
-      double* swin = swinall + warp * wstride;
-      {
-        const double su = a.sqrtu[b];
-        const double* d = a.data + (size_t)b * a.seglen;
-        const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
-        __syncwarp();
-        for (int i = lane; i < TKW + 2 * H; i += 32) {
-          const int64_t sidx = kbase - H + i;
-          double v = 0.0;
-          if (sidx >= lo && sidx < hi) v = __ldg(d + (sidx - a.seg0)) * su;
-          swin[i] = v;
-        }
-        __syncwarp();
-      }
-      double win[W + KT - 1];
-#pragma unroll
-      for (int e = 0; e < W + KT - 1; e++) win[e] = swin[lane * KT + e];
-      for (int g = g0; g < g1; g++, step++) {
-        double z[KT];
-#ifdef BFL_WS_NOCORR
-#pragma unroll
-        for (int j = 0; j < KT; j++) z[j] = win[j] * 0.9 + win[j + 1] * 0.3 + 0.01 * (g - gb);
-#else
-        correlate_reg<W, KT>(stmpl + (size_t)(g - gb) * WP, win, z);
-#endif
-        const int slot = step % WS_D;
-        mbar_wait(empty + slot, ((step / WS_D) & 1) ^ 1);
-        double* dst = ring + (size_t)slot * KT * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < KT; j++) dst[j * 32] = z[j];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + slot);
-      }
-    } else {
-      // ---- consumer c: every KT samples of the lane, templates of parity c (within the chunk).
-      // Each consumer keeps its own partial log-sum-exp; the two are merged by k_combine
-      // (sub-chunk index = consumer index).
-      const double hlv = a.halflogv[b];
-      const int64_t kfirst = kbase + (int64_t)lane * KT;
-      bool valid[KT];
-#pragma unroll
-      for (int j = 0; j < KT; j++) {
-        const int64_t k = kfirst + j;
-        valid[j] = (k < a.k1) && (k >= H) && (k < a.N - H);
-      }
-      int h = 0;
-      while (a.hyp_begin[h + 1] <= g0) h++;
-      double mx[KT], sm[KT];
-#pragma unroll
-      for (int j = 0; j < KT; j++) { mx[j] = LSE_EMPTY; sm[j] = 0.0; }
-      auto flush = [&](int hh) {
-        if (MODE == 0) {
-          const double hc = (a.hyp_half[hh] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv;
-          double2* pp = a.part + ((size_t)(hh * a.NC * WS_NC + chunk * WS_NC + c) * a.B + b) * nk;
-#pragma unroll
-          for (int j = 0; j < KT; j++) {
-            if (valid[j]) pp[kfirst + j - a.k0] = make_double2(mx[j] + hc, sm[j]);
-            mx[j] = LSE_EMPTY; sm[j] = 0.0;
+            for (int j = 0; j < KT; j++) zc[j] = yB[j];
           }
+        } else {
+          correlate(g - gb, zc);
         }
-      };
-      for (int g = g0; g < g1; g++, step++) {
-        while (g >= a.hyp_begin[h + 1]) { flush(h); h++; }
-        const int slot = step % WS_D;
-        if (((g - g0) & 1) != c) continue;                      // the other consumer's template
         const bool half = a.hyp_half[h] != 0;
         const double* tab = sphi + (half ? 0 : BFL_PHI_STRIDE);
         const double kg = sK[g - gb];
-        mbar_wait(full + slot, (step / WS_D) & 1);
-        const double* src = ring + (size_t)slot * KT * 32 + lane;
-        double zc[KT];
-#pragma unroll
-        for (int j = 0; j < KT; j++) zc[j] = src[j * 32];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + slot);
-#ifdef BFL_WS_NOEPI
-#pragma unroll
-        for (int j = 0; j < KT; j++) mx[j] += zc[j];
-        continue;
-#endif
         double val[KT];
         bool far_ = false;
 #pragma unroll
@@ -752,12 +586,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_window_ws(const FastArgs a) {
           val[j] = kg + phi_tab(zc[j], tab);
           far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
         }
-        if (half && far_) {
+        if (half && far_) {   // rare: a > 12 sigma negative amplitude
 #pragma unroll
           for (int j = 0; j < KT; j++)
             if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
         }
-        if (MODE == 0) {
+        if (MODE != 1) {
 #pragma unroll
           for (int j = 0; j < KT; j++) lse_push(mx[j], sm[j], val[j], st64);
         } else {
@@ -771,37 +605,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_window_ws(const FastArgs a) {
           }
         }
       }
-      flush(h);
     }
+    flush(h);
   }
-}
-
-static size_t ws_smem_bytes(int gchunk) {
-  const int WP = WS_W + 1;
-  const int wstride = (32 * WS_KT + 2 * (WS_W / 2) + 2) & ~1;
-  return sizeof(double) * (size_t)(WS_NP * wstride + WS_NP * WS_D * WS_KT * 32 + 2 * WS_NP * WS_D +
-                                   (size_t)gchunk * WP + ((gchunk + 1) & ~1) + 2 * BFL_PHI_STRIDE + 64);
-}
-
-template <int MODE>
-static cudaError_t launch_ws_impl(FastArgs& a, cudaStream_t s, LaunchStats* st) {
-  const size_t smem = ws_smem_bytes(a.gchunk);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (MODE == 2) {
+    double* o = a.lnO + (size_t)b * nk;
+#pragma unroll
+    for (int j = 0; j < KT; j++)
+      if (valid[j]) o[kfirst + j - a.k0] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
   }
-  cudaError_t e = cudaFuncSetAttribute(k_window_ws<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int64_t gx = (sms + a.NC - 1) / a.NC;
-  const int64_t need = (a.total_wtiles + WS_NP - 1) / WS_NP;
-  if (gx > need) gx = need;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)a.NC);
-  k_window_ws<MODE><<<grid, WS_THREADS, smem, s>>>(a);
-  st->launches++;
-  return cudaGetLastError();
+  }   // warp-tile loop
 }
 
 size_t fast_smem_bytes(int W, int gchunk, int KT) {
@@ -809,6 +622,15 @@ size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(gchunk + 1) * WP + ((gchunk + 1) & ~1) +
                                    2 * BFL_PHI_STRIDE + 64);
+}
+
+// separable-grid form: S shape rows instead of G template rows, per-template scalars, per-thread A slice
+size_t fast_sep_smem_bytes(int W, int G, int S, int KT) {
+  const int WP = W + 1;
+  const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
+  return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(S + 1) * WP + 2 * ((G + 1) & ~1) +
+                                   2 * BFL_PHI_STRIDE + 64 + (size_t)SEP_MAXA * KT * FAST_TPB) +
+         sizeof(short) * (size_t)((2 * G + 7) & ~7);
 }
 
 // choose samples-per-thread and the template chunk so that the grid covers the chip
@@ -854,11 +676,13 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
   for (int h = 0; h < pv.nhyp; h++) a.hyp_half[h] = pv.hyp_half[h];
   a.part = sc.part;
   a.out_full = nullptr; a.bgabs = sc.bgabs; a.sls = 0.0; a.ihyp = 0; a.lnO = nullptr; a.noisepoly = 0;
+  a.shapes = pv.shapes; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB; a.S = pv.S;
+  for (int h = 0; h < pv.nhyp; h++) { a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
 }
 
 template <int MODE>
-static cudaError_t launch_fast_impl(FastArgs& a, int KT, cudaStream_t s, LaunchStats* st) {
-  const size_t smem = fast_smem_bytes(a.W, a.gchunk, KT);
+static cudaError_t launch_fast_impl(FastArgs& a, int KT, bool sep, cudaStream_t s, LaunchStats* st) {
+  const size_t smem = sep ? fast_sep_smem_bytes(a.W, a.G, a.S, KT) : fast_smem_bytes(a.W, a.gchunk, KT);
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -867,13 +691,13 @@ static cudaError_t launch_fast_impl(FastArgs& a, int KT, cudaStream_t s, LaunchS
   }
   cudaError_t e = cudaSuccess;
   // persistent grid: as many CTAs as the device holds at once (or fewer if there is less work)
-#define BFL_LAUNCH(WT_, KT_)                                                                              \
+#define BFL_LAUNCH(WT_, KT_, SEP_)                                                                        \
   do {                                                                                                    \
-    e = cudaFuncSetAttribute(k_window_fast<WT_, KT_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)smem);                                                                  \
+    auto kern = k_window_fast<WT_, KT_, MODE, SEP_>;                                                      \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return e;                                                                       \
     int occ = 1;                                                                                          \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_window_fast<WT_, KT_, MODE>, FAST_TPB, smem); \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FAST_TPB, smem);                        \
     if (e != cudaSuccess) return e;                                                                       \
     if (occ < 1) occ = 1;                                                                                 \
     int64_t gx = ((int64_t)sms * occ + a.NC - 1) / a.NC;                                                  \
@@ -881,30 +705,29 @@ static cudaError_t launch_fast_impl(FastArgs& a, int KT, cudaStream_t s, LaunchS
     if (gx > need) gx = need;                                                                             \
     if (gx < 1) gx = 1;                                                                                   \
     dim3 grid((unsigned)gx, (unsigned)a.NC);                                                              \
-    k_window_fast<WT_, KT_, MODE><<<grid, FAST_TPB, smem, s>>>(a);                                        \
+    kern<<<grid, FAST_TPB, smem, s>>>(a);                                                                 \
   } while (0)
-  if (a.W == 55 && KT == 8) BFL_LAUNCH(55, 8);
-  else if (a.W == 55 && KT == 4) BFL_LAUNCH(55, 4);
-  else if (a.W == 55 && KT == 2) BFL_LAUNCH(55, 2);
-  else if (a.W == 55 && KT == 1) BFL_LAUNCH(55, 1);
-  else BFL_LAUNCH(0, 1);
+  if (sep) {
+    if (KT == 4) BFL_LAUNCH(55, 4, true);
+    else if (KT == 2) BFL_LAUNCH(55, 2, true);
+    else BFL_LAUNCH(55, 1, true);
+  } else if (a.W == 55 && KT == 8) BFL_LAUNCH(55, 8, false);
+  else if (a.W == 55 && KT == 4) BFL_LAUNCH(55, 4, false);
+  else if (a.W == 55 && KT == 2) BFL_LAUNCH(55, 2, false);
+  else if (a.W == 55 && KT == 1) BFL_LAUNCH(55, 1, false);
+  else BFL_LAUNCH(0, 1, false);
 #undef BFL_LAUNCH
   st->launches++;
   return cudaGetLastError();
 }
 
-// the warp-specialised kernel targets the large-batch case (W = 55, KT = 4, enough tiles for every SM)
-bool fast_uses_ws(int W, int KT, int gchunk);
-static bool use_ws(const FastArgs& a, int KT) { return fast_uses_ws(a.W, KT, a.gchunk); }
-bool fast_uses_ws(int W, int KT, int gchunk) {
-  // Opt-in (BFL_WS=1).  Measured on B200 (round 1): 3.50 ms against 3.13 ms for the single-role
-  // persistent kernel on the 1,024-curve batch -- producers and consumers end up waiting on each
-  // other (30 % of stall samples sit in the mbarrier wait), so it is kept as an experiment only.
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("BFL_WS"); enabled = (e && atoi(e)) ? 1 : 0; }
-  if (!enabled) return false;
-  return W == WS_W && KT == WS_KT && ws_smem_bytes(gchunk) <= 200 * 1024;
+// the separable form needs the whole plan in one CTA (NC == 1) and W == 55
+bool fast_sep_fits(const PlanView& pv, int KT) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("BFL_NO_SEP"); off = (e && atoi(e)) ? 1 : 0; }
+  return !off && pv.sep_ok && KT <= 4 && fast_sep_smem_bytes(pv.W, pv.G, pv.S, KT) <= 220 * 1024;
 }
+static bool use_sep(const PlanView& pv, const Scratch& sc, int KT) { return sc.NC == 1 && fast_sep_fits(pv, KT); }
 
 static int kt_for(const PlanView& pv, const SeriesView& sv, const Scratch& sc) {
   (void)pv; (void)sv;
@@ -917,8 +740,7 @@ cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scr
   FastArgs a;
   const int KT = kt_for(pv, sv, sc);
   fill_fast_args(a, pv, sv, sc, KT);
-  if (use_ws(a, KT)) return launch_ws_impl<0>(a, s, st);
-  return launch_fast_impl<0>(a, KT, s, st);
+  return launch_fast_impl<0>(a, KT, use_sep(pv, sc, KT), s, st);
 }
 
 // fused detector: log odds straight from the window kernel (no partials, no combine launch).
@@ -934,7 +756,7 @@ cudaError_t launch_window_fast_fused(const PlanView& pv, const SeriesView& sv, S
   const int KT = kt_for(pv, sv, sc);
   fill_fast_args(a, pv, sv, sc, KT);
   a.lnO = d_lnO; a.noisepoly = noisepoly;
-  return launch_fast_impl<2>(a, KT, s, st);
+  return launch_fast_impl<2>(a, KT, use_sep(pv, sc, KT), s, st);
 }
 
 cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
@@ -944,8 +766,7 @@ cudaError_t launch_window_fast_full(const PlanView& pv, int ihyp, const SeriesVi
   const int KT = kt_for(pv, sv, sc);
   fill_fast_args(a, pv, sv, sc, KT);
   a.out_full = d_out; a.sls = sumlogsigma; a.ihyp = ihyp;
-  if (use_ws(a, KT)) return launch_ws_impl<1>(a, s, st);
-  return launch_fast_impl<1>(a, KT, s, st);
+  return launch_fast_impl<1>(a, KT, use_sep(pv, sc, KT), s, st);
 }
 
 // --------------------------------------------------------------------------------------

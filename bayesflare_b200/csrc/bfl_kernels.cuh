@@ -33,7 +33,20 @@ struct PlanView {
   const double* bb;          // [P*(P+1)/2][WP] products b_p*b_q (upper triangle, row-major)
   const double* qb;          // [P][WP] orthonormalised background basis
   double logdetG;            // log det of the unit-variance background Gram matrix
+  // ---- separable-grid form (see k_window_fast, SEP): template g = shape A[idxA[g]] + shape B[idxB[g]]
+  // (orthogonalised, un-normalised), z_g = inorm[g] * (yA + yB).  Dense hypotheses have idxA = -1 and
+  // their own normalised template as shape B.
+  int sep_ok;                // the whole plan fits one CTA in this form
+  int S;                     // number of shape vectors
+  const double* shapes;      // [S][WP]
+  const double* inorm;       // [G]
+  const short* idxA;         // [G] index into the hypothesis' A shapes, or -1
+  const short* idxB;         // [G] global shape index
+  int hyp_A0[MAXH];          // global shape index of the hypothesis' first A shape
+  int hyp_nA[MAXH];          // number of A shapes (0: dense hypothesis)
 };
+
+constexpr int SEP_MAXA = 16;   // A shapes per hypothesis the kernel keeps per thread in shared memory
 
 struct SeriesView {
   const double* clc;    // dev [B][seglen]
@@ -65,7 +78,10 @@ struct LaunchStats { int64_t launches = 0; };
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
                                  double* d_raw, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_plan_orthonormalise(const double* d_raw, const double* d_qb, int G, int W, int WP, int P,
-                                       double* d_hat, double* d_Kg, cudaStream_t s, LaunchStats* st);
+                                       double* d_hat, double* d_Kg, double* d_inorm, int normalise, cudaStream_t s,
+                                       LaunchStats* st);
+// A_i <- A_i - C for the separable form (rows [a0, a0+nA) minus row c of a [.][WP] array)
+cudaError_t launch_subtract_row(double* d_rows, int a0, int nA, int c, int WP, cudaStream_t s, LaunchStats* st);
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st);
 // polynomial-only factor for interior constant-variance samples (fast path)
@@ -113,7 +129,8 @@ cudaError_t launch_tv_sigma(const double* d_resid, int64_t N, int B, double sigm
 cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
 
 size_t fast_smem_bytes(int W, int gchunk, int KT);
-bool fast_uses_ws(int W, int KT, int gchunk);
+size_t fast_sep_smem_bytes(int W, int G, int S, int KT);
+bool fast_sep_fits(const PlanView& pv, int KT);
 int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out);
 
 }  // namespace bfl

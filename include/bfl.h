@@ -93,6 +93,10 @@ int bfl_plan_destroy(bfl_plan* plan);
 /* device-generated templates of hypothesis ihyp -> host out[ngrid][W] (masked rows are zero).
  * Equivalent of Model.__call__(q, ts=mts).clc (model.py:133-153). */
 int bfl_plan_templates(bfl_plan* plan, int ihyp, double* out);
+/* number of correlation shapes the window kernel evaluates per sample for this plan: fewer than the
+ * number of templates when a flare grid is held in separable form; -1 if the plan
+ * is only available in dense form.  Used by bench.py to report the flops actually executed. */
+int bfl_plan_shape_count(const bfl_plan* plan);
 
 /* ---- Bayes.bayes_factors_marg_poly_bgd / _only (bayes.py:153-563) --------------------
  * replaces log_marg_amp_full_model / _2Dmodel / _background (general.pyx:143-365) and
