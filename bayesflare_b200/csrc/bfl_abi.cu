@@ -429,6 +429,14 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
     sc.gchunk = std::max(pv.G, 1);
   sc.KT = KT;
   sc.NC = (std::max(pv.G, 1) + sc.gchunk - 1) / sc.gchunk;
+  sc.Y = nullptr;
+  if (sv.const_var && sc.NC == 1 && KT <= 4 && sc.gchunk == std::max(pv.G, 1) && fast_split_fits(pv) &&
+      (int64_t)sv.B * nk >= (int64_t)32 * KT * 2 * c->sm_count) {
+    void* yp;
+    int rcy = c->get("Y", sizeof(double) * (size_t)pv.S * sv.B * nk, &yp);
+    if (rcy) return rcy;
+    sc.Y = (double*)yp;       // large batch: split form (correlation kernel + epilogue kernel)
+  }
   sc.sub = 1;
   int rc;
   void* ptr;
@@ -489,14 +497,16 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   if (fused) {
     std::pair<cudaEvent_t, cudaEvent_t> pr;
     if (c->timing && (rc = timing_begin(c, pr))) return rc;
-    CK(launch_window_fast_fused(pv, sv, sc, noisepoly, d_lnO, s, &c->stats));
+    if (sc.Y) CK(launch_window_split(pv, sv, sc, 2, noisepoly, d_lnO, s, &c->stats));
+    else CK(launch_window_fast_fused(pv, sv, sc, noisepoly, d_lnO, s, &c->stats));
     if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
     return BFL_OK;
   }
   if (sv.const_var) {
     std::pair<cudaEvent_t, cudaEvent_t> pr;
     if (c->timing && (rc = timing_begin(c, pr))) return rc;
-    CK(launch_window_fast_lse(pv, sv, sc, s, &c->stats));
+    if (sc.Y) CK(launch_window_split(pv, sv, sc, 0, noisepoly, nullptr, s, &c->stats));
+    else CK(launch_window_fast_lse(pv, sv, sc, s, &c->stats));
     if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
     if (need_bg) CK(launch_bgproj(pv, sv, sc, s, &c->stats));
     if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));

@@ -54,28 +54,23 @@ __device__ __forceinline__ double phi_half(double z) {
 
 #include "phi_table.inc"
 
-// phi(z) from the piecewise degree-6 table (tools/gen_phi_table.py; |error| < 2e-14), `tab` is the
-// shared-memory copy laid out [coefficient][interval].  Straight-line code: the interval index is
-// clamped, and because the last interval is stored as the exact quadratic z^2/2 + log 2 (erfc = 2
-// to 1e-19 there) clamping extrapolates correctly for any larger z.  Only z < -12.06 needs the
-// erfcx form (phi_half_far), which callers apply in a rarely-taken fix-up branch.
-// A second table block holds the full-range function z^2/2 in the same format, so both kinds of
-// hypothesis run the same instruction stream with a different table offset.
+// phi(z) from the piecewise polynomial table (tools/gen_phi_table.py: degree 4 on intervals of 1/32,
+// |error| < 1.3e-13), `tab` is the shared-memory copy laid out [coefficient][interval].  Straight-line
+// code: the interval index is clamped, and because the last interval is stored as the exact quadratic
+// z^2/2 + log 2 (erfc = 2 to 1e-19 there) clamping extrapolates correctly for any larger z.  Only
+// z < BFL_PHI_ZFAR needs the erfcx form (phi_half_far), which callers apply in a rarely-taken fix-up
+// branch.  Full-range hypotheses need no table: their function is z^2/2.
 #define BFL_PHI_STRIDE ((BFL_PHI_DEG + 1) * BFL_PHI_NI)
-#define BFL_PHI_ZFAR (-12.0625)
+#define BFL_PHI_ZFAR (BFL_PHI_ZMIN - 0.5 / BFL_PHI_INVH)
 __device__ __forceinline__ double phi_tab(double z, const double* __restrict__ tab) {
   const double s = fma(z, BFL_PHI_INVH, -(BFL_PHI_ZMIN) * BFL_PHI_INVH);
   int k = __double2int_rn(s);
   k = min(max(k, 0), BFL_PHI_NI - 1);
   const double x = s - (double)k;
   const double* c = tab + k;
-  double v = c[6 * BFL_PHI_NI];
-  v = fma(v, x, c[5 * BFL_PHI_NI]);
-  v = fma(v, x, c[4 * BFL_PHI_NI]);
-  v = fma(v, x, c[3 * BFL_PHI_NI]);
-  v = fma(v, x, c[2 * BFL_PHI_NI]);
-  v = fma(v, x, c[1 * BFL_PHI_NI]);
-  v = fma(v, x, c[0]);
+  double v = c[BFL_PHI_DEG * BFL_PHI_NI];
+#pragma unroll
+  for (int i = BFL_PHI_DEG - 1; i >= 0; i--) v = fma(v, x, c[i * BFL_PHI_NI]);
   return v;
 }
 __device__ __noinline__ double phi_half_far(double z) {   // z < -12.06: log erfcx(-z/sqrt2)
@@ -396,8 +391,8 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   double* sdata = smem;                                  // [WPB][wstride]
   double* stmpl = smem + (FAST_TPB / 32) * wstride;      // [nrows + 1][WP] (last row: zeros)
   double* sK = stmpl + (size_t)(nrows + 1) * WP;         // [gchunk]  Kg + lp (+ lw)
-  double* sphi = sK + ((a.gchunk + 1) & ~1);             // [2][(DEG+1) * NI] phi(z) and z^2/2 tables
-  double* st64 = sphi + 2 * BFL_PHI_STRIDE;              // [64] 2^(j/64)
+  double* sphi = sK + ((a.gchunk + 1) & ~1);             // [(DEG+1) * NI] phi(z) table
+  double* st64 = sphi + BFL_PHI_STRIDE;                  // [64] 2^(j/64)
   double* sInorm = st64 + 64;                            // SEP: [gchunk] 1/|m_perp|
   short* sIdx = reinterpret_cast<short*>(sInorm + (SEP ? ((a.gchunk + 1) & ~1) : 0));   // SEP: [gchunk][2] (A, B)
   double* ysm = reinterpret_cast<double*>(sIdx + (SEP ? ((2 * a.gchunk + 7) & ~7) : 0)); // SEP: [SEP_MAXA][KT][FAST_TPB]
@@ -421,13 +416,7 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
       }
     }
     if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
-    for (int i = tid; i < BFL_PHI_STRIDE; i += FAST_TPB) {
-      sphi[i] = BFL_PHI_TAB[i];
-      // full-range hypotheses: z^2/2 in the same per-interval format (exact quadratic)
-      const int c = i / BFL_PHI_NI, kk = i - c * BFL_PHI_NI;
-      const double zk = BFL_PHI_ZMIN + kk * (1.0 / BFL_PHI_INVH), hh = 1.0 / BFL_PHI_INVH;
-      sphi[BFL_PHI_STRIDE + i] = (c == 0) ? 0.5 * zk * zk : (c == 1) ? zk * hh : (c == 2) ? 0.5 * hh * hh : 0.0;
-    }
+    for (int i = tid; i < BFL_PHI_STRIDE; i += FAST_TPB) sphi[i] = BFL_PHI_TAB[i];
   }
   __syncthreads();
 
@@ -577,19 +566,23 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
           correlate(g - gb, zc);
         }
         const bool half = a.hyp_half[h] != 0;
-        const double* tab = sphi + (half ? 0 : BFL_PHI_STRIDE);
         const double kg = sK[g - gb];
         double val[KT];
-        bool far_ = false;
+        if (half) {
+          bool far_ = false;
 #pragma unroll
-        for (int j = 0; j < KT; j++) {
-          val[j] = kg + phi_tab(zc[j], tab);
-          far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
-        }
-        if (half && far_) {   // rare: a > 12 sigma negative amplitude
+          for (int j = 0; j < KT; j++) {
+            val[j] = kg + phi_tab(zc[j], sphi);
+            far_ = far_ || (zc[j] < BFL_PHI_ZFAR);
+          }
+          if (far_) {   // rare: a > 12 sigma negative amplitude
 #pragma unroll
-          for (int j = 0; j < KT; j++)
-            if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
+            for (int j = 0; j < KT; j++)
+              if (zc[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(zc[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < KT; j++) val[j] = fma(0.5 * zc[j], zc[j], kg);
         }
         if (MODE != 1) {
 #pragma unroll
@@ -617,11 +610,295 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   }   // warp-tile loop
 }
 
+// ======================================================================================
+// FAST path, split form for large batches (W = 55, separable-grid plans)
+// ======================================================================================
+// The correlation wants a big register window (few resident warps); the epilogue (table look-ups,
+// exp, log-sum-exp) is latency/LSU bound and wants many resident warps.  One kernel cannot have both,
+// so large batches run two:
+//   k_corr_shapes : y_s(k) = shape_s . d[k-h .. k+h] for the S shapes of the plan -> Y[s][b*nk + k]
+//   k_epilogue    : one sample per thread lane (SPT samples per thread), z_g = inorm_g (yA + yB),
+//                   phi table, online log-sum-exp per hypothesis, hypotheses combined -> lnO
+// Y makes one round trip through HBM (S * 8 bytes per sample each way), overlapped with the FP64 work.
+struct CorrArgs {
+  const double* data; const double* sqrtu;
+  int64_t seglen, N, seg0, k0, k1;
+  int B, tiles_per_curve;
+  int64_t total_wtiles;
+  unsigned long long* tile_counter;
+  const double* shapes; int S, WP;
+  double* Y;            // [S][B * nk]
+};
+
+template <int KT>
+__global__ void __launch_bounds__(FAST_TPB, 3) k_corr_shapes(const CorrArgs a) {
+  extern __shared__ double smem[];
+  constexpr int W = 55, H = W / 2, TKW = 32 * KT;
+  const int WP = a.WP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int wstride = (TKW + 2 * H + 2) & ~1;
+  double* swin = smem + warp * wstride;
+  double* sshape = smem + (FAST_TPB / 32) * wstride;       // [S][WP]
+  {
+    const double2* src = reinterpret_cast<const double2*>(a.shapes);
+    double2* dst = reinterpret_cast<double2*>(sshape);
+    for (int i = tid; i < a.S * WP / 2; i += FAST_TPB) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int64_t nk = a.k1 - a.k0;
+  const int64_t BK = (int64_t)a.B * nk;
+  for (;;) {
+    long long wt = 0;
+    if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
+    wt = __shfl_sync(0xffffffffu, wt, 0);
+    if (wt >= a.total_wtiles) break;
+    const int tile = (int)(wt % a.tiles_per_curve);
+    const int b = (int)(wt / a.tiles_per_curve);
+    const int64_t kbase = a.k0 + (int64_t)tile * TKW;
+    {
+      const double su = a.sqrtu[b];
+      const double* d = a.data + (size_t)b * a.seglen;
+      const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
+      __syncwarp();
+      for (int i = lane; i < TKW + 2 * H; i += 32) {
+        const int64_t sidx = kbase - H + i;
+        double v = 0.0;
+        if (sidx >= lo && sidx < hi) v = __ldg(d + (sidx - a.seg0)) * su;
+        swin[i] = v;
+      }
+      __syncwarp();
+    }
+    double win[W + KT - 1];
+#pragma unroll
+    for (int e = 0; e < W + KT - 1; e++) win[e] = swin[lane * KT + e];
+    const int64_t kfirst = kbase + (int64_t)lane * KT;
+    bool valid[KT];
+#pragma unroll
+    for (int j = 0; j < KT; j++) {
+      const int64_t k = kfirst + j;
+      valid[j] = (k < a.k1) && (k >= H) && (k < a.N - H);
+    }
+    double* yout = a.Y + (size_t)b * nk + (kfirst - a.k0);
+    for (int sh = 0; sh < a.S; sh++) {
+      double y[KT];
+      correlate_reg<W, KT>(sshape + (size_t)sh * WP, win, y);
+#pragma unroll
+      for (int j = 0; j < KT; j++)
+        if (valid[j]) yout[(size_t)sh * BK + j] = y[j];
+    }
+  }
+}
+
+struct EpiArgs {
+  const double* Y;        // [S][BK]
+  const double* halflogv; // [B]
+  int64_t nk, BK, N, k0;
+  int B, G, nhyp, H;
+  int hyp_begin[MAXH + 1];
+  int hyp_half[MAXH];
+  int hyp_A0[MAXH];
+  int hyp_nA[MAXH];
+  const double* Kg; const double* lp; const double* lw; const double* inorm;
+  const short* idxA; const short* idxB;
+  int noisepoly;
+  double* lnO;            // MODE 2
+  double2* part;          // MODE 0: [nhyp][BK]
+};
+
+constexpr int EPI_TPB = 256;
+
+template <int MODE, int SPT>
+__global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int G = a.G;
+  double* sK = smem;                                     // [G] Kg + lp + lw
+  double* sInorm = sK + ((G + 1) & ~1);                  // [G]
+  double* sphi = sInorm + ((G + 1) & ~1);                // phi table
+  double* st64 = sphi + BFL_PHI_STRIDE;                  // [64]
+  short* sIdx = reinterpret_cast<short*>(st64 + 64);     // [G][2]
+  for (int i = tid; i < G; i += EPI_TPB) {
+    sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
+    sInorm[i] = a.inorm[i];
+    sIdx[2 * i] = a.idxA[i];
+    sIdx[2 * i + 1] = a.idxB[i];
+  }
+  if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+  for (int i = tid; i < BFL_PHI_STRIDE; i += EPI_TPB) sphi[i] = BFL_PHI_TAB[i];
+  __syncthreads();
+
+  const int64_t tile_samples = (int64_t)EPI_TPB * SPT;
+  const int64_t ntiles = (a.BK + tile_samples - 1) / tile_samples;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int64_t idx[SPT];
+    bool valid[SPT];
+    double hlv[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; j++) {
+      idx[j] = tile * tile_samples + (int64_t)j * EPI_TPB + tid;
+      valid[j] = idx[j] < a.BK;
+      if (!valid[j]) idx[j] = a.BK - 1;
+      const int64_t b = idx[j] / a.nk;
+      const int64_t k = a.k0 + (idx[j] - b * a.nk);
+      valid[j] = valid[j] && (k >= a.H) && (k < a.N - a.H);   // interior samples only
+      hlv[j] = a.halflogv[b];
+    }
+    double mx[SPT], sm[SPT], n_m[SPT], n_s[SPT], d_m[SPT], d_s[SPT];
+#pragma unroll
+    for (int j = 0; j < SPT; j++) {
+      mx[j] = LSE_EMPTY; sm[j] = 0.0;
+      n_m[j] = LSE_EMPTY; n_s[j] = 0.0;
+      d_m[j] = a.noisepoly ? 0.0 : LSE_EMPTY; d_s[j] = a.noisepoly ? 1.0 : 0.0;
+    }
+    for (int h = 0; h < a.nhyp; h++) {
+      const int glo = a.hyp_begin[h], ghi = a.hyp_begin[h + 1];
+      if (glo >= ghi) continue;
+      const bool half = a.hyp_half[h] != 0;
+      {
+        // the A-shape correlations of a template are re-read through L1 (each is shared by the
+        // templates of one rise time); the B-shape value stays in registers while it is shared
+        const double* YA = a.Y + (size_t)a.hyp_A0[h] * a.BK;
+        int curB = -1;
+        double yB[SPT];
+        for (int g = glo; g < ghi; g++) {
+          const int ia = sIdx[2 * g], ib = sIdx[2 * g + 1];
+          if (ib != curB) {
+            curB = ib;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) yB[j] = __ldg(a.Y + (size_t)ib * a.BK + idx[j]);
+          }
+          const double kg = sK[g];
+          const double sc = (ia >= 0) ? sInorm[g] : 1.0;
+          double z[SPT], val[SPT];
+#pragma unroll
+          for (int j = 0; j < SPT; j++)
+            z[j] = (ia >= 0) ? sc * (__ldg(YA + (size_t)ia * a.BK + idx[j]) + yB[j]) : yB[j];
+          if (half) {
+            bool far_ = false;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+              val[j] = kg + phi_tab(z[j], sphi);
+              far_ = far_ || (z[j] < BFL_PHI_ZFAR);
+            }
+            if (far_) {
+#pragma unroll
+              for (int j = 0; j < SPT; j++)
+                if (z[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(z[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
+          }
+#pragma unroll
+          for (int j = 0; j < SPT; j++) lse_push(mx[j], sm[j], val[j], st64);
+        }
+      }
+      // hypothesis finished: partial out (MODE 0) or fold into numerator / denominator (MODE 2)
+      const double hcb = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
+#pragma unroll
+      for (int j = 0; j < SPT; j++) {
+        const double x = mx[j] + (hcb + hlv[j]);
+        if (MODE == 0) {
+          if (valid[j]) a.part[(size_t)h * a.BK + idx[j]] = make_double2(x, sm[j]);
+        } else if (h == 0) {
+          n_m[j] = x; n_s[j] = sm[j];
+        } else {
+          const double d = x - d_m[j];
+          const double e = exp_nonpos(-fabs(d), st64);
+          const bool up = d > 0.0;
+          d_s[j] = up ? fma(d_s[j], e, sm[j]) : fma(sm[j], e, d_s[j]);
+          d_m[j] = up ? x : d_m[j];
+        }
+        mx[j] = LSE_EMPTY; sm[j] = 0.0;
+      }
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int j = 0; j < SPT; j++)
+        if (valid[j]) a.lnO[idx[j]] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
+    }
+  }
+}
+
+static size_t corr_smem_bytes(int S, int KT) {
+  const int wstride = (32 * KT + 2 * 27 + 2) & ~1;
+  return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)S * 56);
+}
+static size_t epi_smem_bytes(int G, int SPT) {
+  (void)SPT;
+  return sizeof(double) * (size_t)(2 * ((G + 1) & ~1) + BFL_PHI_STRIDE + 64) + sizeof(short) * (size_t)(2 * G + 8);
+}
+
+bool fast_split_fits(const PlanView& pv) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("BFL_NO_SPLIT"); off = (e && atoi(e)) ? 1 : 0; }
+  return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && epi_smem_bytes(pv.G, 2) <= 200 * 1024;
+}
+
+// mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
+cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
+                                double* d_lnO, cudaStream_t s, LaunchStats* st) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int64_t nk = sv.k1 - sv.k0;
+  const int KT = sc.KT;
+  CorrArgs c;
+  c.data = sv.clc; c.sqrtu = sc.sqrtu; c.seglen = sv.seglen; c.N = sv.N; c.seg0 = sv.seg0; c.k0 = sv.k0; c.k1 = sv.k1;
+  c.B = sv.B; c.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
+  c.total_wtiles = (int64_t)c.tiles_per_curve * sv.B; c.tile_counter = sc.tile_counters;
+  c.shapes = pv.shapes; c.S = pv.S; c.WP = pv.WP; c.Y = sc.Y;
+  const size_t smem1 = corr_smem_bytes(pv.S, KT);
+  cudaError_t e;
+#define BFL_CORR(KT_)                                                                                       \
+  do {                                                                                                      \
+    e = cudaFuncSetAttribute(k_corr_shapes<KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);  \
+    if (e != cudaSuccess) return e;                                                                         \
+    int occ = 1;                                                                                            \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_corr_shapes<KT_>, FAST_TPB, smem1);           \
+    if (e != cudaSuccess) return e;                                                                         \
+    int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);                                                        \
+    const int64_t need = (c.total_wtiles + FAST_TPB / 32 - 1) / (FAST_TPB / 32);                            \
+    if (gx > need) gx = need;                                                                               \
+    k_corr_shapes<KT_><<<(unsigned)(gx < 1 ? 1 : gx), FAST_TPB, smem1, s>>>(c);                             \
+  } while (0)
+  if (KT == 4) BFL_CORR(4); else if (KT == 2) BFL_CORR(2); else BFL_CORR(1);
+#undef BFL_CORR
+  st->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+
+  EpiArgs a;
+  a.Y = sc.Y; a.halflogv = sc.halflogv; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
+  a.B = sv.B; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
+  for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
+  for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
+  a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.noisepoly = noisepoly; a.lnO = d_lnO; a.part = sc.part;
+  constexpr int SPT = 2;
+  const size_t smem2 = epi_smem_bytes(pv.G, SPT);
+  const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
+#define BFL_EPI(MODE_)                                                                                      \
+  do {                                                                                                      \
+    e = cudaFuncSetAttribute(k_epilogue<MODE_, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+    if (e != cudaSuccess) return e;                                                                         \
+    int occ = 1;                                                                                            \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_epilogue<MODE_, SPT>, EPI_TPB, smem2);        \
+    if (e != cudaSuccess) return e;                                                                         \
+    int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);                                                        \
+    if (gx > ntiles) gx = ntiles;                                                                           \
+    k_epilogue<MODE_, SPT><<<(unsigned)(gx < 1 ? 1 : gx), EPI_TPB, smem2, s>>>(a);                          \
+  } while (0)
+  if (mode == 2) BFL_EPI(2); else BFL_EPI(0);
+#undef BFL_EPI
+  st->launches++;
+  return cudaGetLastError();
+}
+
 size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int WP = W + 1;
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(gchunk + 1) * WP + ((gchunk + 1) & ~1) +
-                                   2 * BFL_PHI_STRIDE + 64);
+                                   BFL_PHI_STRIDE + 64);
 }
 
 // separable-grid form: S shape rows instead of G template rows, per-template scalars, per-thread A slice
@@ -629,7 +906,7 @@ size_t fast_sep_smem_bytes(int W, int G, int S, int KT) {
   const int WP = W + 1;
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(S + 1) * WP + 2 * ((G + 1) & ~1) +
-                                   2 * BFL_PHI_STRIDE + 64 + (size_t)SEP_MAXA * KT * FAST_TPB) +
+                                   BFL_PHI_STRIDE + 64 + (size_t)SEP_MAXA * KT * FAST_TPB) +
          sizeof(short) * (size_t)((2 * G + 7) & ~7);
 }
 

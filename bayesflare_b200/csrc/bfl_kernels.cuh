@@ -67,6 +67,7 @@ struct Scratch {
   double2* part;   // [nhyp][NC][B*nk] partial log-sum-exp (max, sum)
   double* bgabs;   // [B*nk] polynomial-only log Bayes factor (no sumlogsigma) or nullptr
   unsigned long long* tile_counters;  // [NC] dynamic tile scheduler state
+  double* Y;       // [S][B*nk] shape correlations (split form) or nullptr
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
@@ -128,6 +129,9 @@ cudaError_t launch_tv_sigma(const double* d_resid, int64_t N, int B, double sigm
                             double* d_sk, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_t s, LaunchStats* st);
 
+bool fast_split_fits(const PlanView& pv);
+cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
+                                double* d_lnO, cudaStream_t s, LaunchStats* st);
 size_t fast_smem_bytes(int W, int gchunk, int KT);
 size_t fast_sep_smem_bytes(int W, int G, int S, int KT);
 bool fast_sep_fits(const PlanView& pv, int KT);
