@@ -55,32 +55,56 @@ __device__ __forceinline__ double phi_half(double z) {
 #include "phi_table.inc"
 
 // phi(z) from the piecewise polynomial table (tools/gen_phi_table.py: degree 4 on intervals of 1/32,
-// |error| < 1.3e-13), `tab` is the shared-memory copy laid out [coefficient][interval].  Straight-line
-// code: the interval index is clamped, and because the last interval is stored as the exact quadratic
-// z^2/2 + log 2 (erfc = 2 to 1e-19 there) clamping extrapolates correctly for any larger z.  Only
-// z < BFL_PHI_ZFAR needs the erfcx form (phi_half_far), which callers apply in a rarely-taken fix-up
-// branch.  Full-range hypotheses need no table: their function is z^2/2.
-#define BFL_PHI_STRIDE ((BFL_PHI_DEG + 1) * BFL_PHI_NI)
+// |error| < 1.3e-13).  `tab` is the shared-memory copy, one 16-byte aligned row of BFL_PHI_ROW doubles
+// per interval, fetched with 128-bit loads (the look-up is lane-varying, so fewer, wider loads mean
+// fewer shared-memory wavefronts).  Straight-line code: the interval index is clamped, and because
+// the last interval is stored as the exact quadratic z^2/2 + log 2 (erfc = 2 to 1e-19 there) clamping
+// extrapolates correctly for any larger z.  Only z < BFL_PHI_ZFAR needs the erfcx form
+// (phi_half_far), which callers apply in a rarely-taken fix-up branch.  Full-range hypotheses need
+// no table: their function is z^2/2.
+#define BFL_PHI_STRIDE (BFL_PHI_ROW * BFL_PHI_NI)            // interval-major copy (epilogue kernel)
+#define BFL_PHI_CM_SIZE ((BFL_PHI_DEG + 1) * BFL_PHI_NI)     // coefficient-major copy (single-kernel path)
 #define BFL_PHI_ZFAR (BFL_PHI_ZMIN - 0.5 / BFL_PHI_INVH)
+static_assert(BFL_PHI_DEG == 4 && BFL_PHI_ROW == 6, "phi_tab* are written for the degree-4 table");
+// (a) coefficient-major shared-memory copy [coef][interval], 64-bit loads: best in the single-kernel path
 __device__ __forceinline__ double phi_tab(double z, const double* __restrict__ tab) {
   const double s = fma(z, BFL_PHI_INVH, -(BFL_PHI_ZMIN) * BFL_PHI_INVH);
   int k = __double2int_rn(s);
   k = min(max(k, 0), BFL_PHI_NI - 1);
   const double x = s - (double)k;
   const double* c = tab + k;
-  double v = c[BFL_PHI_DEG * BFL_PHI_NI];
-#pragma unroll
-  for (int i = BFL_PHI_DEG - 1; i >= 0; i--) v = fma(v, x, c[i * BFL_PHI_NI]);
+  double v = c[4 * BFL_PHI_NI];
+  v = fma(v, x, c[3 * BFL_PHI_NI]);
+  v = fma(v, x, c[2 * BFL_PHI_NI]);
+  v = fma(v, x, c[BFL_PHI_NI]);
+  v = fma(v, x, c[0]);
+  return v;
+}
+// (b) interval-major copy [interval][BFL_PHI_ROW] as generated, three 128-bit loads: fewer shared-memory
+// wavefronts, best in the epilogue kernel (which is bound by these lane-varying look-ups)
+__device__ __forceinline__ double phi_tab_rows(double z, const double* __restrict__ tab) {
+  const double s = fma(z, BFL_PHI_INVH, -(BFL_PHI_ZMIN) * BFL_PHI_INVH);
+  int k = __double2int_rn(s);
+  k = min(max(k, 0), BFL_PHI_NI - 1);
+  const double x = s - (double)k;
+  const double2* c = reinterpret_cast<const double2*>(tab + k * BFL_PHI_ROW);
+  const double2 c01 = c[0], c23 = c[1], c4 = c[2];
+  double v = fma(c4.x, x, c23.y);
+  v = fma(v, x, c23.x);
+  v = fma(v, x, c01.y);
+  v = fma(v, x, c01.x);
   return v;
 }
 __device__ __noinline__ double phi_half_far(double z) {   // z < -12.06: log erfcx(-z/sqrt2)
   return log(erfcx(-z * 0.70710678118654752440));
 }
 
-// e^d for d <= 0 (NaN propagates).  d = (64 e + j) ln2/64 + r with |r| <= ln2/128:
-// e^d = 2^e * 2^(j/64) * e^r; 2^(j/64) comes from a 64-entry shared-memory table (`t64`), e^r from a
-// degree-5 polynomial (relative error < 1e-16), 2^e is patched into the exponent field.
-// Total relative error < 2e-15 (single-constant range reduction), ample for a log-sum-exp.
+// e^d for d <= 0 (NaN propagates), two variants:
+//  * exp_nonpos: d = (64 e + j) ln2/64 + r, |r| <= ln2/128; 2^(j/64) from a 64-entry shared-memory table
+//    (`t64`), e^r from a degree-5 polynomial, 2^e patched into the exponent field (relative error
+//    < 2e-15 where it matters).  Fewest FP64 instructions: used by the single-kernel path.
+//  * exp_nonpos_poly: d = n ln2 + r, |r| <= ln2/2, degree-11 polynomial (relative error < 7e-15), no
+//    table: used by the epilogue kernel, which is bound by lane-varying shared-memory look-ups.
 __device__ __forceinline__ double exp_nonpos(double d, const double* __restrict__ t64) {
   d = (d < -700.0) ? -700.0 : d;
   const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
@@ -98,12 +122,43 @@ __device__ __forceinline__ double exp_nonpos(double d, const double* __restrict_
   return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
 }
 
+__device__ __forceinline__ double exp_nonpos_poly(double d) {
+  d = (d < -700.0) ? -700.0 : d;
+  const double MAGIC = 6755399441055744.0;
+  const double t = fma(d, 1.4426950408889634074, MAGIC);
+  const int n = __double2loint(t);
+  const double nf = t - MAGIC;
+  double r = fma(nf, -6.93147180369123816490e-01, d);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 2.50521083854417187751e-08;      // 1/11!
+  p = fma(p, r, 2.75573192239858906526e-07);
+  p = fma(p, r, 2.75573192239858906526e-06);
+  p = fma(p, r, 2.48015873015873015873e-05);
+  p = fma(p, r, 1.98412698412698412698e-04);
+  p = fma(p, r, 1.38888888888888888889e-03);
+  p = fma(p, r, 8.33333333333333333333e-03);
+  p = fma(p, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 // online log-sum-exp, branch-free: m = running maximum (starts at LSE_EMPTY), s = sum exp(x_i - m)
 #define LSE_EMPTY (-1.0e300)
 __device__ __forceinline__ void lse_push(double& m, double& s, double x, const double* __restrict__ t64) {
   const double d = x - m;
   const double e = exp_nonpos(-fabs(d), t64);
   const bool up = __double2hiint(d) >= 0;     // sign bit (integer pipe); d == 0 gives the same sum either way
+  s = fma(s, up ? e : 1.0, up ? 1.0 : e);
+  m = up ? x : m;
+}
+
+__device__ __forceinline__ void lse_push_poly(double& m, double& s, double x) {
+  const double d = x - m;
+  const double e = exp_nonpos_poly(-fabs(d));
+  const bool up = __double2hiint(d) >= 0;
   s = fma(s, up ? e : 1.0, up ? 1.0 : e);
   m = up ? x : m;
 }
@@ -330,7 +385,7 @@ struct FastArgs {
   int noisepoly;          // FUSED mode
   // separable-grid form (SEP kernels)
   const double* shapes; const double* inorm; const short* idxA; const short* idxB;
-  int S;
+  int S, arows;
   int hyp_A0[MAXH];
   int hyp_nA[MAXH];
 };
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
   double* stmpl = smem + (FAST_TPB / 32) * wstride;      // [nrows + 1][WP] (last row: zeros)
   double* sK = stmpl + (size_t)(nrows + 1) * WP;         // [gchunk]  Kg + lp (+ lw)
   double* sphi = sK + ((a.gchunk + 1) & ~1);             // [(DEG+1) * NI] phi(z) table
-  double* st64 = sphi + BFL_PHI_STRIDE;                  // [64] 2^(j/64)
+  double* st64 = sphi + BFL_PHI_CM_SIZE;                 // [64] 2^(j/64)
   double* sInorm = st64 + 64;                            // SEP: [gchunk] 1/|m_perp|
   short* sIdx = reinterpret_cast<short*>(sInorm + (SEP ? ((a.gchunk + 1) & ~1) : 0));   // SEP: [gchunk][2] (A, B)
   double* ysm = reinterpret_cast<double*>(sIdx + (SEP ? ((2 * a.gchunk + 7) & ~7) : 0)); // SEP: [SEP_MAXA][KT][FAST_TPB]
@@ -416,7 +471,10 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
       }
     }
     if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
-    for (int i = tid; i < BFL_PHI_STRIDE; i += FAST_TPB) sphi[i] = BFL_PHI_TAB[i];
+    for (int i = tid; i < (BFL_PHI_DEG + 1) * BFL_PHI_NI; i += FAST_TPB) {   // [coef][interval] copy
+      const int cidx = i / BFL_PHI_NI, kk = i - cidx * BFL_PHI_NI;
+      sphi[i] = BFL_PHI_TAB[kk * BFL_PHI_ROW + cidx];
+    }
   }
   __syncthreads();
 
@@ -715,15 +773,13 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
   double* sK = smem;                                     // [G] Kg + lp + lw
   double* sInorm = sK + ((G + 1) & ~1);                  // [G]
   double* sphi = sInorm + ((G + 1) & ~1);                // phi table
-  double* st64 = sphi + BFL_PHI_STRIDE;                  // [64]
-  short* sIdx = reinterpret_cast<short*>(st64 + 64);     // [G][2]
+  short* sIdx = reinterpret_cast<short*>(sphi + BFL_PHI_STRIDE);   // [G][2]
   for (int i = tid; i < G; i += EPI_TPB) {
     sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
     sInorm[i] = a.inorm[i];
     sIdx[2 * i] = a.idxA[i];
     sIdx[2 * i + 1] = a.idxB[i];
   }
-  if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
   for (int i = tid; i < BFL_PHI_STRIDE; i += EPI_TPB) sphi[i] = BFL_PHI_TAB[i];
   __syncthreads();
 
@@ -777,7 +833,7 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
             bool far_ = false;
 #pragma unroll
             for (int j = 0; j < SPT; j++) {
-              val[j] = kg + phi_tab(z[j], sphi);
+              val[j] = kg + phi_tab_rows(z[j], sphi);
               far_ = far_ || (z[j] < BFL_PHI_ZFAR);
             }
             if (far_) {
@@ -790,7 +846,7 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
             for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
           }
 #pragma unroll
-          for (int j = 0; j < SPT; j++) lse_push(mx[j], sm[j], val[j], st64);
+          for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
         }
       }
       // hypothesis finished: partial out (MODE 0) or fold into numerator / denominator (MODE 2)
@@ -804,7 +860,7 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
           n_m[j] = x; n_s[j] = sm[j];
         } else {
           const double d = x - d_m[j];
-          const double e = exp_nonpos(-fabs(d), st64);
+          const double e = exp_nonpos_poly(-fabs(d));
           const bool up = d > 0.0;
           d_s[j] = up ? fma(d_s[j], e, sm[j]) : fma(sm[j], e, d_s[j]);
           d_m[j] = up ? x : d_m[j];
@@ -826,7 +882,7 @@ static size_t corr_smem_bytes(int S, int KT) {
 }
 static size_t epi_smem_bytes(int G, int SPT) {
   (void)SPT;
-  return sizeof(double) * (size_t)(2 * ((G + 1) & ~1) + BFL_PHI_STRIDE + 64) + sizeof(short) * (size_t)(2 * G + 8);
+  return sizeof(double) * (size_t)(2 * ((G + 1) & ~1) + BFL_PHI_STRIDE) + sizeof(short) * (size_t)(2 * G + 8);
 }
 
 bool fast_split_fits(const PlanView& pv) {
@@ -898,16 +954,23 @@ size_t fast_smem_bytes(int W, int gchunk, int KT) {
   const int WP = W + 1;
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(gchunk + 1) * WP + ((gchunk + 1) & ~1) +
-                                   BFL_PHI_STRIDE + 64);
+                                   BFL_PHI_CM_SIZE + 64);
 }
 
 // separable-grid form: S shape rows instead of G template rows, per-template scalars, per-thread A slice
-size_t fast_sep_smem_bytes(int W, int G, int S, int KT) {
+size_t fast_sep_smem_bytes(int W, int G, int S, int KT, int arows) {
   const int WP = W + 1;
   const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)(S + 1) * WP + 2 * ((G + 1) & ~1) +
-                                   BFL_PHI_STRIDE + 64 + (size_t)SEP_MAXA * KT * FAST_TPB) +
+                                   BFL_PHI_CM_SIZE + 64 + (size_t)arows * KT * FAST_TPB) +
          sizeof(short) * (size_t)((2 * G + 7) & ~7);
+}
+
+// A-shape rows the per-thread shared-memory slice must hold: the largest hypothesis, capped by SEP_MAXA
+static int sep_arows(const PlanView& pv) {
+  int m = 1;
+  for (int h = 0; h < pv.nhyp; h++) m = std::max(m, std::min(pv.hyp_nA[h], SEP_MAXA));
+  return m;
 }
 
 // choose samples-per-thread and the template chunk so that the grid covers the chip
@@ -953,13 +1016,13 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
   for (int h = 0; h < pv.nhyp; h++) a.hyp_half[h] = pv.hyp_half[h];
   a.part = sc.part;
   a.out_full = nullptr; a.bgabs = sc.bgabs; a.sls = 0.0; a.ihyp = 0; a.lnO = nullptr; a.noisepoly = 0;
-  a.shapes = pv.shapes; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB; a.S = pv.S;
+  a.shapes = pv.shapes; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB; a.S = pv.S; a.arows = sep_arows(pv);
   for (int h = 0; h < pv.nhyp; h++) { a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
 }
 
 template <int MODE>
 static cudaError_t launch_fast_impl(FastArgs& a, int KT, bool sep, cudaStream_t s, LaunchStats* st) {
-  const size_t smem = sep ? fast_sep_smem_bytes(a.W, a.G, a.S, KT) : fast_smem_bytes(a.W, a.gchunk, KT);
+  const size_t smem = sep ? fast_sep_smem_bytes(a.W, a.G, a.S, KT, a.arows) : fast_smem_bytes(a.W, a.gchunk, KT);
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -1002,7 +1065,7 @@ static cudaError_t launch_fast_impl(FastArgs& a, int KT, bool sep, cudaStream_t 
 bool fast_sep_fits(const PlanView& pv, int KT) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_SEP"); off = (e && atoi(e)) ? 1 : 0; }
-  return !off && pv.sep_ok && KT <= 4 && fast_sep_smem_bytes(pv.W, pv.G, pv.S, KT) <= 220 * 1024;
+  return !off && pv.sep_ok && KT <= 4 && fast_sep_smem_bytes(pv.W, pv.G, pv.S, KT, sep_arows(pv)) <= 220 * 1024;
 }
 static bool use_sep(const PlanView& pv, const Scratch& sc, int KT) { return sc.NC == 1 && fast_sep_fits(pv, KT); }
 

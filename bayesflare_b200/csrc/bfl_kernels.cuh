@@ -133,7 +133,7 @@ bool fast_split_fits(const PlanView& pv);
 cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
                                 double* d_lnO, cudaStream_t s, LaunchStats* st);
 size_t fast_smem_bytes(int W, int gchunk, int KT);
-size_t fast_sep_smem_bytes(int W, int G, int S, int KT);
+size_t fast_sep_smem_bytes(int W, int G, int S, int KT, int arows);
 bool fast_sep_fits(const PlanView& pv, int KT);
 int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out);
 
