@@ -312,11 +312,12 @@ def run_ours(args, rank, local_rank, world):
     interior = N - 2 * (det.bglen // 2)
     flops_launch = float(B) * interior * (N_TEMPLATES * FLOP_PER_UNIT + FLOP_SHARED_PER_SAMPLE)
     flops_strict = float(B) * interior * N_TEMPLATES * 2.0 * det.bglen
-    # what the kernel really executes: the flare grid is held in separable form (rise x decay shapes), so
-    # only `shapes` correlations of 2W flop are done per sample, plus ~2 flop to assemble z and ~40 flop
-    # of epilogue (phi table polynomial, exp, log-sum-exp update) per template
+    # what the kernels really execute: the flare grid is held in separable form (rise x decay shapes), so
+    # only `shapes` correlations of 2W flop are done per sample (k_corr_shapes), plus per template ~2 flop
+    # to assemble z and ~52 flop of epilogue (degree-4 phi polynomial, degree-11 exp, log-sum-exp update;
+    # k_epilogue)
     shapes = plan.shape_count if plan.shape_count > 0 else N_TEMPLATES
-    flops_exec = float(B) * interior * (shapes * 2.0 * det.bglen + N_TEMPLATES * 42.0)
+    flops_exec = float(B) * interior * (shapes * 2.0 * det.bglen + N_TEMPLATES * 54.0)
     win_avg_ms = win_ms / max(win_n, 1)
     achieved = flops_launch / (win_avg_ms * 1e-3) / 1e12
     peaks = {}
@@ -334,7 +335,7 @@ def run_ours(args, rank, local_rank, world):
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": traffic, "kernel": "k_window_fast<55,4,FUSED,SEP>", "kernel_ms": win_avg_ms,
+                "traffic": traffic, "kernel": "window stage = k_corr_shapes<4> + k_epilogue<FUSED,2> (split form; both launches inside kernel_ms)", "kernel_ms": win_avg_ms,
                 "kernel_share_of_step": win_ms / ms_total,
                 "peak_source": "measured live by bfl_fp64_peak_probe (16 independent DFMA chains/thread, burst); "
                                "FP64 is not in MEASURED_PEAKS.json",
