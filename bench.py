@@ -53,7 +53,7 @@ class ClockSampler(threading.Thread):
             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
