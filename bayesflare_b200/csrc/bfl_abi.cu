@@ -303,6 +303,7 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
     if (sep) {
       const int A0 = S, B0 = S + (int)tgs.size(), C = B0 + (int)tes.size();
       pv.hyp_A0[h] = A0; pv.hyp_nA[h] = (int)tgs.size();
+      pv.hyp_B0[h] = B0; pv.hyp_nB[h] = (int)tes.size();
       for (size_t i = 0; i < tgs.size(); i++) {
         TemplDesc d = desc[g0]; d.p[1] = 0.0; d.p[2] = tgs[i];
         sdesc.push_back(d); sdesc_at.push_back(A0 + (int)i);
@@ -319,6 +320,7 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
       sub_c.push_back({A0, (int)tgs.size(), C});
       S = C + 1;
     } else {
+      pv.hyp_B0[h] = S; pv.hyp_nB[h] = g1 - g0;
       for (int g = g0; g < g1; g++) { dense_src.push_back(g); dense_at.push_back(S); idxB[g] = (short)S; S++; }
     }
     if (S > 30000) sep_ok = false;
@@ -359,6 +361,8 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
     CKP(cudaMemcpyAsync((double*)d_raw + (size_t)table_at[i] * WP, table_rows.data() + i * W, sizeof(double) * (size_t)W,
                         cudaMemcpyHostToDevice, s));
   void *d_inorm = nullptr, *d_shapes = nullptr, *d_idxA = nullptr, *d_idxB = nullptr;
+  void *d_rshapes = nullptr, *d_shlo = nullptr, *d_shhi = nullptr;
+  bool wsep_ok = false;
   if ((rc = plan_alloc(p, sizeof(double) * (size_t)std::max(G, 1), &d_inorm))) { bfl_plan_destroy(p); return rc; }
   CKP(launch_plan_orthonormalise((const double*)d_raw, (const double*)d_qb, G, W, WP, P, (double*)d_hat,
                                  (double*)d_Kg, (double*)d_inorm, 1, s, &c->stats));
@@ -385,12 +389,55 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
     for (size_t i = 0; i < dense_src.size(); i++)
       CKP(cudaMemcpyAsync((double*)d_shapes + (size_t)dense_at[i] * WP, (double*)d_hat + (size_t)dense_src[i] * WP,
                           sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
+    // raw-template shapes for the weighted path: A_i = m(tg_i, 0) - m(0, 0) (rise only), B_j = m(0, te_j)
+    if ((rc = plan_alloc(p, sizeof(double) * (size_t)S * WP, &d_rshapes)) ||
+        (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shlo)) || (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shhi))) {
+      bfl_plan_destroy(p);
+      return rc;
+    }
+    CKP(cudaMemsetAsync(d_rshapes, 0, sizeof(double) * (size_t)S * WP, s));
+    for (int i = 0; i < ns; i++)
+      CKP(cudaMemcpyAsync((double*)d_rshapes + (size_t)sdesc_at[i] * WP, (double*)d_sraw + (size_t)i * WP,
+                          sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
+    for (auto& ac : sub_c) CKP(launch_subtract_row((double*)d_rshapes, ac.a0, ac.na, ac.c, WP, s, &c->stats));
+    for (size_t i = 0; i < dense_src.size(); i++)
+      CKP(cudaMemcpyAsync((double*)d_rshapes + (size_t)dense_at[i] * WP, (double*)d_raw + (size_t)dense_src[i] * WP,
+                          sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
+    std::vector<double> hs((size_t)S * WP);
+    CKP(cudaMemcpyAsync(hs.data(), d_rshapes, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, s));
+    CKP(cudaStreamSynchronize(s));
+    std::vector<short> lo(S, 0), hi(S, 0);
+    for (int r = 0; r < S; r++) {
+      int a = W, b = 0;
+      for (int w = 0; w < W; w++)
+        if (hs[(size_t)r * WP + w] != 0.0) { a = std::min(a, w); b = std::max(b, w + 1); }   // NaN counts as non-zero
+      if (b <= a) { a = WP; b = 0; }   // empty shape (tau_gauss = 0 rise): contributes nothing to a group's span
+      lo[r] = (short)(a & ~1); hi[r] = (short)b;
+    }
+    // the weighted norm separates only if rise and decay never overlap; templates must be grouped by B shape
+    wsep_ok = (WP % 2) == 0;
+    for (int h = 0; h < nhyp && wsep_ok; h++) {
+      for (int g = pv.hyp_begin[h] + 1; g < pv.hyp_begin[h + 1]; g++)
+        if (idxB[g] < idxB[g - 1]) wsep_ok = false;
+      for (int ia = 0; ia < pv.hyp_nA[h] && wsep_ok; ia++)
+        for (int ib = 0; ib < pv.hyp_nB[h] && wsep_ok; ib++)
+          for (int w = 0; w < W; w++)
+            if (hs[(size_t)(pv.hyp_A0[h] + ia) * WP + w] != 0.0 && hs[(size_t)(pv.hyp_B0[h] + ib) * WP + w] != 0.0) {
+              wsep_ok = false;
+              break;
+            }
+    }
+    CKP(cudaMemcpyAsync(d_shlo, lo.data(), sizeof(short) * (size_t)S, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_shhi, hi.data(), sizeof(short) * (size_t)S, cudaMemcpyHostToDevice, s));
+    CKP(cudaStreamSynchronize(s));
   }
   CKP(cudaStreamSynchronize(s));   // host vectors above go out of scope
 #undef CKP
   pv.sep_ok = (sep_ok && G > 0) ? 1 : 0;
   pv.shapes = (const double*)d_shapes; pv.inorm = (const double*)d_inorm;
   pv.idxA = (const short*)d_idxA; pv.idxB = (const short*)d_idxB;
+  pv.wsep_ok = (pv.sep_ok && wsep_ok) ? 1 : 0;
+  pv.rshapes = (const double*)d_rshapes; pv.sh_lo = (const short*)d_shlo; pv.sh_hi = (const short*)d_shhi;
   pv.raw = (const double*)d_raw; pv.hat = (const double*)d_hat; pv.Kg = (const double*)d_Kg;
   pv.lp = (const double*)d_lp; pv.lw = (const double*)d_lw; pv.gorig = (const int*)d_gorig;
   pv.bg = (const double*)d_bg; pv.bb = (const double*)d_bb; pv.qb = (const double*)d_qb;
@@ -419,7 +466,7 @@ int bfl_plan_templates(bfl_plan* p, int ihyp, double* out) {
 
 // --------------------------------------------------------------------------------------
 static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, bool need_general, bool need_bg,
-                         bool need_part, Scratch& sc) {
+                         bool need_part, Scratch& sc, bool one_chunk = false) {
   const int64_t nk = sv.k1 - sv.k0;
   int KT = 1;
   sc.gchunk = pick_gchunk(std::max(pv.G, 1), pv.W, (int64_t)sv.B * nk, c->sm_count, &KT);
@@ -427,6 +474,7 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   // small problems keep the template-chunked dense form, which spreads one curve over all SMs
   if (sv.const_var && fast_sep_fits(pv, KT) && (int64_t)sv.B * nk >= (int64_t)32 * KT * 2 * c->sm_count)
     sc.gchunk = std::max(pv.G, 1);
+  if (one_chunk) sc.gchunk = std::max(pv.G, 1);
   sc.KT = KT;
   sc.NC = (std::max(pv.G, 1) + sc.gchunk - 1) / sc.gchunk;
   sc.Y = nullptr;
@@ -489,9 +537,11 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   const bool need_bg = (d_marg != nullptr) || nnoise == 0;
   Scratch sc{};
   // first pass without the partial-sum buffer: it is not needed when the kernel can fuse the combine
-  if ((rc = setup_scratch(c, pv, sv, need_general, need_bg, false, sc))) return rc;
+  // per-sample variances: the separable weighted kernel keeps the whole plan in one CTA
+  const bool wsep = !sv.const_var && wsep_fits(pv);
+  if ((rc = setup_scratch(c, pv, sv, need_general, need_bg, false, sc, wsep))) return rc;
   const bool fused = sv.const_var && !edges && !need_bg && fast_can_fuse(pv, sc, noisepoly);
-  if (!fused && (rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc))) return rc;
+  if (!fused && (rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc, wsep))) return rc;
   cudaStream_t s = c->stream;
   CK(launch_prep(sv, sc, need_general, s, &c->stats));
   if (fused) {
@@ -509,6 +559,13 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
     else CK(launch_window_fast_lse(pv, sv, sc, s, &c->stats));
     if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
     if (need_bg) CK(launch_bgproj(pv, sv, sc, s, &c->stats));
+    if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));
+  } else if (wsep || weighted_fits(pv, sc)) {
+    std::pair<cudaEvent_t, cudaEvent_t> pr;
+    if (c->timing && (rc = timing_begin(c, pr))) return rc;
+    if (wsep) CK(launch_window_wsep_lse(pv, sv, sc, s, &c->stats));
+    else CK(launch_window_weighted_lse(pv, sv, sc, s, &c->stats));
+    if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
     if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));
   } else {
     CK(launch_window_general_lse(pv, sv, sc, false, s, &c->stats));
@@ -727,6 +784,9 @@ int bfl_window_lnB(bfl_ctx* c, bfl_plan* p, int ihyp, const double* clc, const d
   if (cv) {
     CK(launch_bgproj(pv, sv, sc, s, &c->stats));
     if (ihyp >= 0) CK(launch_window_fast_full(pv, ihyp, sv, sc, sumlogsigma, (double*)d_out, s, &c->stats));
+    CK(launch_window_general_full(pv, ihyp, sv, sc, true, sumlogsigma, (double*)d_out, s, &c->stats));
+  } else if (weighted_fits(pv, sc)) {
+    CK(launch_window_weighted_full(pv, ihyp, sv, sc, sumlogsigma, (double*)d_out, s, &c->stats));
     CK(launch_window_general_full(pv, ihyp, sv, sc, true, sumlogsigma, (double*)d_out, s, &c->stats));
   } else {
     CK(launch_window_general_full(pv, ihyp, sv, sc, false, sumlogsigma, (double*)d_out, s, &c->stats));

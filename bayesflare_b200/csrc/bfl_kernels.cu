@@ -1298,6 +1298,7 @@ struct GenArgs {
   const double* raw; const double* lp; const double* lw; const int* gorig;
   const double* bg; const double* bb;
   int G, W, WP, gchunk, NC, nhyp, sub;
+  int tm_global;        // templates read from global memory (chunk too large for shared memory)
   int hyp_begin[MAXH + 1];
   int hyp_half[MAXH];
   double2* part;
@@ -1321,14 +1322,16 @@ __global__ void k_window_general(const GenArgs a) {
   double* sbg = smem;                       // [P][WP]
   double* sbb = sbg + P * WP;               // [NPAIR][WP]
   double* stm = sbb + NPAIR * WP;           // [gchunk][WP]
-  double* swu = stm + (size_t)a.gchunk * WP;// [W][TPB]  noise-variance window, transposed
+  double* swu = stm + (size_t)(a.tm_global ? 0 : a.gchunk) * WP;   // [W][TPB]  noise-variance window, transposed
   double* swd = swu + (size_t)W * TPB;      // [W][TPB]  d/v window, transposed
   double* st64 = swd + (size_t)W * TPB;     // [64] 2^(j/64) for the log-sum-exp
   for (int i = tid; i < 64; i += TPB) st64[i] = exp2((double)i * (1.0 / 64.0));
 
   for (int i = tid; i < P * WP; i += TPB) sbg[i] = a.bg[i];
   for (int i = tid; i < NPAIR * WP; i += TPB) sbb[i] = a.bb[i];
-  for (int i = tid; i < (ge - gb) * WP; i += TPB) stm[i] = a.raw[(size_t)gb * WP + i];
+  if (!a.tm_global)
+    for (int i = tid; i < (ge - gb) * WP; i += TPB) stm[i] = a.raw[(size_t)gb * WP + i];
+  const double* tmpl = a.tm_global ? a.raw + (size_t)gb * WP : stm;
 
   // which sample does this thread own?
   int64_t k;
@@ -1391,7 +1394,7 @@ __global__ void k_window_general(const GenArgs a) {
     const bool half = a.hyp_half[h] != 0;
     double mx = LSE_EMPTY, sm = 0.0;
     for (int g = lo; g < hi; g++) {
-      const double* m = stm + (size_t)(g - gb) * WP + w0;
+      const double* m = tmpl + (size_t)(g - gb) * WP + w0;
       // model x model (bayes.py:367-377), model x background (bayes.py:380-393)
       const double mm = pairwise_np(n, [&](int i) { return div_(mul_(m[i], m[i]), swu[(w0 + i) * TPB + tid]); });
       double mdbg[P];
@@ -1424,7 +1427,8 @@ static size_t general_smem(int P, int W, int gchunk, int tpb) {
 
 template <int MODE>
 static cudaError_t launch_general_impl(GenArgs& a, int P, cudaStream_t s, LaunchStats* st) {
-  const size_t smem = general_smem(P, a.W, a.gchunk, a.tpb);
+  a.tm_global = general_smem(P, a.W, a.gchunk, a.tpb) > 200 * 1024 ? 1 : 0;
+  const size_t smem = general_smem(P, a.W, a.tm_global ? 0 : a.gchunk, a.tpb);
   dim3 grid((unsigned)(a.tiles_per_curve * a.B), (unsigned)a.NC);
   cudaError_t e = cudaSuccess;
 #define BFL_GL(P_)                                                                                        \
@@ -1472,6 +1476,609 @@ cudaError_t launch_window_general_full(const PlanView& pv, int ihyp, const Serie
   fill_gen_args(a, pv, sv, sc, edges_only);
   a.out_full = d_out; a.sls = sumlogsigma; a.ihyp = ihyp;
   return launch_general_impl<1>(a, pv.P, s, st);
+}
+
+// ======================================================================================
+// WEIGHTED path: interior samples of a curve with per-sample variances v_j = sk^2 + cle_j^2
+// ======================================================================================
+// Same integral as the general path (bayes.py:315-407 -> general.pyx:143-246 -> log_marg_amp_full_C),
+// evaluated in the orthonormal polynomial basis Q of the plan, where the system is well conditioned
+// (full windows only -- the truncated edge windows keep the reference-order arithmetic above):
+//   A = Q U Q^T (P x P), c = Q U d, per template e = m^T U m, f = Q U m, r0 = m^T U d, U = diag(1/v)
+//   A = L L^T, yc = L^-1 c, yf = L^-1 f, s = e - |yf|^2, r = r0 - yf.yc, z = r / sqrt(s)
+//   lnB_bg = -0.5 logdet(G) - sum log L_ii + 0.5 |yc|^2 + 0.5 P log 2 pi
+//   lnB_g - lnB_bg = -0.5 log s + { 0.5 log(pi/2) + phi(z) | 0.5 log(2 pi) + z^2/2 }
+// One thread per sample; the 1/v and d/v tiles (+ halo) live in shared memory and are read with
+// lane-consecutive (conflict-free) loads, Q and the templates with broadcast 128-bit loads; WGT_GT
+// templates share each pass over the window, so a pass is (P+2) WGT_GT FMAs per tap against
+// (2 + (P + WGT_GT)/2) shared-memory loads.  Algorithmic work: (P + 2) W FMAs per (sample, template).
+struct WgtArgs {
+  const double* dw;     // [B][seglen]  d / v
+  const double* uu;     // [B][seglen]  v
+  int64_t seglen, N, seg0, k0, k1;
+  int B, tiles_per_curve;
+  const double* raw; const double* qb; const double* lp; const double* lw; const int* gorig;
+  int G, W, WP, gchunk, NC, nhyp, sub;
+  int hyp_begin[MAXH + 1];
+  int hyp_half[MAXH];
+  double logdetG;
+  double2* part;
+  double* bgabs;
+  double* out_full;
+  double sls;
+  int ihyp;
+};
+
+constexpr int WGT_TPB = 128, WGT_GT = 4;
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(WGT_TPB) k_window_weighted(const WgtArgs a) {
+  extern __shared__ double smem[];
+  const int W = a.W, H = W / 2, WP = a.WP;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % a.tiles_per_curve, b = blockIdx.x / a.tiles_per_curve;
+  const int chunk = blockIdx.y;
+  const int gb = chunk * a.gchunk, ge = min(a.G, gb + a.gchunk);
+  const int nd = (WGT_TPB + 2 * H + 2) & ~1;
+  double* su = smem;                               // [nd] 1/v
+  double* sud = su + nd;                           // [nd] d/v
+  double* sq = sud + nd;                           // [P][WP]
+  double* stm = sq + P * WP;                       // [gchunk][WP]
+  double* sphi = stm + (size_t)a.gchunk * WP;      // [(DEG+1) * NI]
+  double* st64 = sphi + BFL_PHI_CM_SIZE;           // [64]
+
+  const int64_t kbase = a.k0 + (int64_t)tile * WGT_TPB;
+  {
+    const double* du = a.uu + (size_t)b * a.seglen;
+    const double* dd = a.dw + (size_t)b * a.seglen;
+    const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
+    for (int i = tid; i < WGT_TPB + 2 * H; i += WGT_TPB) {
+      const int64_t sidx = kbase - H + i;
+      const bool in = sidx >= lo && sidx < hi;
+      su[i] = in ? 1.0 / du[sidx - a.seg0] : 0.0;
+      sud[i] = in ? dd[sidx - a.seg0] : 0.0;
+    }
+    for (int i = tid; i < P * WP; i += WGT_TPB) sq[i] = a.qb[i];
+    for (int i = tid; i < (ge - gb) * WP; i += WGT_TPB) stm[i] = a.raw[(size_t)gb * WP + i];
+    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+    for (int i = tid; i < BFL_PHI_CM_SIZE; i += WGT_TPB) {
+      const int cidx = i / BFL_PHI_NI, kk = i - cidx * BFL_PHI_NI;
+      sphi[i] = BFL_PHI_TAB[kk * BFL_PHI_ROW + cidx];
+    }
+  }
+  __syncthreads();
+  const int64_t k = kbase + tid;
+  if (k >= a.k1 || k < H || k >= a.N - H) return;      // interior samples only
+  const int64_t nk = a.k1 - a.k0;
+  const int64_t ki = (int64_t)b * nk + (k - a.k0);
+  const double* uw = su + tid;
+  const double* dw = sud + tid;
+
+  // ---- shared by every template of this sample: A = Q U Q^T, c = Q U d ----
+  double L[P][P], inv[P], yc[P];
+  double logdetA = 0.0, quad = 0.0;
+  {
+    double A[P][P], c[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      c[p] = 0.0;
+#pragma unroll
+      for (int q = 0; q < P; q++) A[p][q] = 0.0;
+    }
+    for (int j = 0; j < W; j++) {
+      const double u = uw[j], ud = dw[j];
+      double qv[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) qv[p] = sq[p * WP + j];
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const double uq = u * qv[p];
+        c[p] = fma(ud, qv[p], c[p]);
+#pragma unroll
+        for (int q = p; q < P; q++) A[p][q] = fma(uq, qv[q], A[p][q]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      double d = A[i][i];
+#pragma unroll
+      for (int t = 0; t < i; t++) d = fma(-L[i][t], L[i][t], d);
+      logdetA += log(d);
+      const double r = rsqrt(d);
+      inv[i] = r;
+      L[i][i] = d * r;
+#pragma unroll
+      for (int rr = i + 1; rr < P; rr++) {
+        double x = A[i][rr];
+#pragma unroll
+        for (int t = 0; t < i; t++) x = fma(-L[rr][t], L[i][t], x);
+        L[rr][i] = x * r;
+      }
+      double y = c[i];
+#pragma unroll
+      for (int t = 0; t < i; t++) y = fma(-L[i][t], yc[t], y);
+      yc[i] = y * r;
+      quad = fma(yc[i], yc[i], quad);
+    }
+  }
+  double lnBbg = -0.5 * a.logdetG - 0.5 * logdetA + 0.5 * quad + 0.5 * P * (BFL_LN2 + BFL_LNPI);
+  if (!isfinite(lnBbg)) lnBbg = neg_inf();          // non-finite data or variances, log_marg_amp_full.c:20,25
+  if (chunk == 0 && a.bgabs) a.bgabs[ki] = lnBbg;
+
+  const int h_lo = (MODE == 0) ? 0 : max(a.ihyp, 0);
+  const int h_hi = (MODE == 0) ? a.nhyp : a.ihyp + 1;
+  const int NP2 = W / 2;
+  for (int h = h_lo; h < h_hi; h++) {
+    const int lo = max(gb, a.hyp_begin[h]), hi = min(ge, a.hyp_begin[h + 1]);
+    if (lo >= hi) continue;
+    const bool half = a.hyp_half[h] != 0;
+    const double hc = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
+    double mx = LSE_EMPTY, sm = 0.0;
+    for (int g4 = lo; g4 < hi; g4 += WGT_GT) {
+      const double* mrow[WGT_GT];
+#pragma unroll
+      for (int t = 0; t < WGT_GT; t++) mrow[t] = stm + (size_t)(min(g4 + t, hi - 1) - gb) * WP;
+      double e[WGT_GT], r0[WGT_GT], f[WGT_GT][P];
+#pragma unroll
+      for (int t = 0; t < WGT_GT; t++) {
+        e[t] = 0.0; r0[t] = 0.0;
+#pragma unroll
+        for (int p = 0; p < P; p++) f[t][p] = 0.0;
+      }
+      for (int j2 = 0; j2 < NP2; j2++) {
+        const double u0 = uw[2 * j2], u1 = uw[2 * j2 + 1], d0 = dw[2 * j2], d1 = dw[2 * j2 + 1];
+        double2 qv[P];
+#pragma unroll
+        for (int p = 0; p < P; p++) qv[p] = reinterpret_cast<const double2*>(sq + p * WP)[j2];
+#pragma unroll
+        for (int t = 0; t < WGT_GT; t++) {
+          const double2 m = reinterpret_cast<const double2*>(mrow[t])[j2];
+          const double w0 = u0 * m.x, w1 = u1 * m.y;
+          e[t] = fma(w0, m.x, e[t]); e[t] = fma(w1, m.y, e[t]);
+          r0[t] = fma(d0, m.x, r0[t]); r0[t] = fma(d1, m.y, r0[t]);
+#pragma unroll
+          for (int p = 0; p < P; p++) { f[t][p] = fma(w0, qv[p].x, f[t][p]); f[t][p] = fma(w1, qv[p].y, f[t][p]); }
+        }
+      }
+      {
+        const int j = W - 1;
+        const double u0 = uw[j], d0 = dw[j];
+#pragma unroll
+        for (int t = 0; t < WGT_GT; t++) {
+          const double m = mrow[t][j];
+          const double w0 = u0 * m;
+          e[t] = fma(w0, m, e[t]);
+          r0[t] = fma(d0, m, r0[t]);
+#pragma unroll
+          for (int p = 0; p < P; p++) f[t][p] = fma(w0, sq[p * WP + j], f[t][p]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < WGT_GT; t++) {
+        const int g = g4 + t;
+        if (g >= hi) break;
+        double s = e[t], r = r0[t];
+        double yf[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          double y = f[t][i];
+#pragma unroll
+          for (int q = 0; q < i; q++) y = fma(-L[i][q], yf[q], y);
+          yf[i] = y * inv[i];
+          s = fma(-yf[i], yf[i], s);
+          r = fma(-yf[i], yc[i], r);
+        }
+        const double z = r * rsqrt(s);
+        double val;
+        if (half) {
+          val = phi_tab(z, sphi);
+          if (z < BFL_PHI_ZFAR) val = phi_half_far(z);
+        } else {
+          val = 0.5 * z * z;
+        }
+        val += hc - 0.5 * log(s);
+        if (lnBbg == neg_inf()) val = lnBbg - lnBbg;      // NaN, as (-inf) - (-inf) in the general path
+        if (MODE == 0) {
+          lse_push(mx, sm, val + (a.lp[g] + a.lw[g]), st64);
+        } else {
+          a.out_full[(size_t)a.gorig[g] * nk + (k - a.k0)] =
+              (lnBbg == neg_inf()) ? lnBbg : ((val + lnBbg) + a.sls) + a.lp[g];
+        }
+      }
+    }
+    if (MODE == 0) {
+      a.part[(size_t)((h * a.NC + chunk) * a.sub) * a.B * nk + ki] = make_double2(mx, sm);
+      for (int u = 1; u < a.sub; u++)
+        a.part[(size_t)((h * a.NC + chunk) * a.sub + u) * a.B * nk + ki] = make_double2(LSE_EMPTY, 0.0);
+    }
+  }
+}
+
+static size_t weighted_smem(int P, int W, int gchunk) {
+  const int WP = W + 1;
+  const int nd = (WGT_TPB + 2 * (W / 2) + 2) & ~1;
+  return sizeof(double) * ((size_t)2 * nd + (size_t)(P + gchunk) * WP + BFL_PHI_CM_SIZE + 64);
+}
+
+bool weighted_fits(const PlanView& pv, const Scratch& sc) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("BFL_NO_WEIGHTED"); off = (e && atoi(e)) ? 1 : 0; }
+  return !off && pv.P >= 1 && pv.P <= 6 && (pv.WP % 2) == 0 && weighted_smem(pv.P, pv.W, sc.gchunk) <= 220 * 1024;
+}
+
+template <int MODE>
+static cudaError_t launch_weighted_impl(WgtArgs& a, int P, cudaStream_t s, LaunchStats* st) {
+  const size_t smem = weighted_smem(P, a.W, a.gchunk);
+  dim3 grid((unsigned)(a.tiles_per_curve * a.B), (unsigned)a.NC);
+  cudaError_t e = cudaSuccess;
+#define BFL_WL(P_)                                                                                        \
+  case P_:                                                                                                \
+    e = cudaFuncSetAttribute(k_window_weighted<P_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                             (int)smem);                                                                  \
+    if (e != cudaSuccess) return e;                                                                       \
+    k_window_weighted<P_, MODE><<<grid, WGT_TPB, smem, s>>>(a);                                           \
+    break;
+  switch (P) {
+    BFL_WL(1) BFL_WL(2) BFL_WL(3) BFL_WL(4) BFL_WL(5) BFL_WL(6)
+    default: return cudaErrorInvalidValue;
+  }
+#undef BFL_WL
+  st->launches++;
+  return cudaGetLastError();
+}
+
+static void fill_wgt_args(WgtArgs& a, const PlanView& pv, const SeriesView& sv, const Scratch& sc) {
+  a.dw = sc.dw; a.uu = sc.uu;
+  a.seglen = sv.seglen; a.N = sv.N; a.seg0 = sv.seg0; a.k0 = sv.k0; a.k1 = sv.k1; a.B = sv.B;
+  a.tiles_per_curve = (int)((sv.k1 - sv.k0 + WGT_TPB - 1) / WGT_TPB);
+  a.raw = pv.raw; a.qb = pv.qb; a.lp = pv.lp; a.lw = pv.lw; a.gorig = pv.gorig;
+  a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.gchunk = sc.gchunk; a.NC = sc.NC; a.nhyp = pv.nhyp; a.sub = sc.sub;
+  for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
+  for (int h = 0; h < pv.nhyp; h++) a.hyp_half[h] = pv.hyp_half[h];
+  a.logdetG = pv.logdetG;
+  a.part = sc.part; a.bgabs = sc.bgabs; a.out_full = nullptr; a.sls = 0.0; a.ihyp = 0;
+}
+
+cudaError_t launch_window_weighted_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
+                                       LaunchStats* st) {
+  WgtArgs a;
+  fill_wgt_args(a, pv, sv, sc);
+  return launch_weighted_impl<0>(a, pv.P, s, st);
+}
+
+cudaError_t launch_window_weighted_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
+                                        double sumlogsigma, double* d_out, cudaStream_t s, LaunchStats* st) {
+  WgtArgs a;
+  fill_wgt_args(a, pv, sv, sc);
+  a.out_full = d_out; a.sls = sumlogsigma; a.ihyp = ihyp;
+  return launch_weighted_impl<1>(a, pv.P, s, st);
+}
+
+// --------------------------------------------------------------------------------------
+// WEIGHTED path, separable form (PlanView::rshapes).  A Flare template is rise (+) centre (+) decay on
+// disjoint supports, so with m_g = A_i + B_j every weighted sum separates -- including the norm:
+//   e_g = e_Ai + e_Bj,  f_g = f_Ai + f_Bj,  r0_g = r0_Ai + r0_Bj
+// and the triangular solve is linear, so per SHAPE (not per template) the kernel forms
+//   y = L^-1 f,  s' = e - |y|^2,  r' = r0 - y.yc
+// leaving s_g = s'_A + s'_B - 2 yA.yB, r_g = r'_A + r'_B per template.  The -0.5 log s_g term rides
+// along as a weight 1/sqrt(s_g) in the log-sum-exp, so a template costs P+4 flops, one rsqrt, the
+// phi look-up and one exp.  Shapes are summed over their support only (27 taps for a rise, 28 for
+// a decay, 1 for an impulse).  One thread per sample; A-shape results live in a per-thread
+// shared-memory slice, B shapes are handled WSEP_GT at a time in registers.
+struct WsepArgs {
+  const double* dw; const double* uu;
+  int64_t seglen, N, seg0, k0, k1;
+  int B, tiles_per_curve;
+  const double* rshapes; const short* sh_lo; const short* sh_hi;
+  const double* qb; const double* lp; const double* lw; const short* idxA; const short* idxB;
+  int G, W, WP, S, nhyp, arows;
+  int hyp_begin[MAXH + 1];
+  int hyp_half[MAXH];
+  int hyp_A0[MAXH], hyp_nA[MAXH], hyp_B0[MAXH], hyp_nB[MAXH];
+  double logdetG;
+  double2* part;
+  double* bgabs;
+};
+
+constexpr int WSEP_TPB = 256, WSEP_GT = 4;
+
+// weighted log-sum-exp: s accumulates w_i exp(x_i - m)
+__device__ __forceinline__ void lse_push_w(double& m, double& s, double x, double w, const double* __restrict__ t64) {
+  const double d = x - m;
+  const double e = exp_nonpos(-fabs(d), t64);
+  const bool up = __double2hiint(d) >= 0;
+  s = up ? fma(s, e, w) : fma(w, e, s);
+  m = up ? x : m;
+}
+
+template <int P>
+__global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
+  extern __shared__ double smem[];
+  constexpr int NV = P + 2;                        // per shape: y[P], s', r'
+  const int W = a.W, H = W / 2, WP = a.WP;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % a.tiles_per_curve, b = blockIdx.x / a.tiles_per_curve;
+  const int nd = (WSEP_TPB + 2 * H + 2) & ~1;
+  double* su = smem;                               // [nd] 1/v
+  double* sud = su + nd;                           // [nd] d/v
+  double* sq = sud + nd;                           // [P][WP]
+  double* ssh = sq + P * WP;                       // [S][WP]
+  double* sK = ssh + (size_t)a.S * WP;             // [G] lp + lw
+  double* sphi = sK + ((a.G + 1) & ~1);            // [(DEG+1) * NI]
+  double* st64 = sphi + BFL_PHI_CM_SIZE;           // [64]
+  double* ysm = st64 + 64;                         // [arows][NV][TPB]
+  short* sIdx = reinterpret_cast<short*>(ysm + (size_t)a.arows * NV * WSEP_TPB);   // [G][2]
+  short* sLoHi = sIdx + ((2 * a.G + 7) & ~7);      // [S][2]
+
+  const int64_t kbase = a.k0 + (int64_t)tile * WSEP_TPB;
+  {
+    const double* du = a.uu + (size_t)b * a.seglen;
+    const double* dd = a.dw + (size_t)b * a.seglen;
+    const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
+    for (int i = tid; i < nd; i += WSEP_TPB) {
+      const int64_t sidx = kbase - H + i;
+      const bool in = i < WSEP_TPB + 2 * H && sidx >= lo && sidx < hi;
+      su[i] = in ? 1.0 / du[sidx - a.seg0] : 0.0;
+      sud[i] = in ? dd[sidx - a.seg0] : 0.0;
+    }
+    for (int i = tid; i < P * WP; i += WSEP_TPB) sq[i] = a.qb[i];
+    for (int i = tid; i < a.S * WP; i += WSEP_TPB) ssh[i] = a.rshapes[i];
+    for (int i = tid; i < a.G; i += WSEP_TPB) {
+      sK[i] = a.lp[i] + a.lw[i];
+      sIdx[2 * i] = a.idxA[i];
+      sIdx[2 * i + 1] = a.idxB[i];
+    }
+    for (int i = tid; i < a.S; i += WSEP_TPB) { sLoHi[2 * i] = a.sh_lo[i]; sLoHi[2 * i + 1] = a.sh_hi[i]; }
+    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+    for (int i = tid; i < BFL_PHI_CM_SIZE; i += WSEP_TPB) {
+      const int cidx = i / BFL_PHI_NI, kk = i - cidx * BFL_PHI_NI;
+      sphi[i] = BFL_PHI_TAB[kk * BFL_PHI_ROW + cidx];
+    }
+  }
+  __syncthreads();
+  const int64_t k = kbase + tid;
+  if (k >= a.k1 || k < H || k >= a.N - H) return;      // interior samples only
+  const int64_t nk = a.k1 - a.k0;
+  const int64_t ki = (int64_t)b * nk + (k - a.k0);
+  const double* uw = su + tid;
+  const double* dw = sud + tid;
+
+  // ---- A = Q U Q^T = L L^T, yc = L^-1 Q U d ----
+  double L[P][P], inv[P], yc[P];
+  double logdetA = 0.0, quad = 0.0;
+  {
+    double A[P][P], c[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      c[p] = 0.0;
+#pragma unroll
+      for (int q = 0; q < P; q++) A[p][q] = 0.0;
+    }
+    for (int j = 0; j < W; j++) {
+      const double u = uw[j], ud = dw[j];
+      double qv[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) qv[p] = sq[p * WP + j];
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const double uq = u * qv[p];
+        c[p] = fma(ud, qv[p], c[p]);
+#pragma unroll
+        for (int q = p; q < P; q++) A[p][q] = fma(uq, qv[q], A[p][q]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      double d = A[i][i];
+#pragma unroll
+      for (int t = 0; t < i; t++) d = fma(-L[i][t], L[i][t], d);
+      logdetA += log(d);
+      const double r = rsqrt(d);
+      inv[i] = r;
+      L[i][i] = d * r;
+#pragma unroll
+      for (int rr = i + 1; rr < P; rr++) {
+        double x = A[i][rr];
+#pragma unroll
+        for (int t = 0; t < i; t++) x = fma(-L[rr][t], L[i][t], x);
+        L[rr][i] = x * r;
+      }
+      double y = c[i];
+#pragma unroll
+      for (int t = 0; t < i; t++) y = fma(-L[i][t], yc[t], y);
+      yc[i] = y * r;
+      quad = fma(yc[i], yc[i], quad);
+    }
+  }
+  double lnBbg = -0.5 * a.logdetG - 0.5 * logdetA + 0.5 * quad + 0.5 * P * (BFL_LN2 + BFL_LNPI);
+  const bool bad = !isfinite(lnBbg);
+  if (bad) lnBbg = neg_inf();
+  if (a.bgabs) a.bgabs[ki] = lnBbg;
+
+  // weighted sums of WSEP_GT shapes over the union of their supports, reduced to (y, s', r')
+  auto shape_group = [&](int s0, int smax, double (&V)[WSEP_GT][NV]) {
+    const double* row[WSEP_GT];
+    int lo = WP, hi = 0;
+#pragma unroll
+    for (int t = 0; t < WSEP_GT; t++) {
+      const int si = min(s0 + t, smax);
+      row[t] = ssh + (size_t)si * WP;
+      lo = min(lo, (int)sLoHi[2 * si]);
+      hi = max(hi, (int)sLoHi[2 * si + 1]);
+    }
+    double e[WSEP_GT], r0[WSEP_GT], f[WSEP_GT][P];
+#pragma unroll
+    for (int t = 0; t < WSEP_GT; t++) {
+      e[t] = 0.0; r0[t] = 0.0;
+#pragma unroll
+      for (int p = 0; p < P; p++) f[t][p] = 0.0;
+    }
+    for (int j2 = lo >> 1; j2 < (hi >> 1); j2++) {
+      const double u0 = uw[2 * j2], u1 = uw[2 * j2 + 1], d0 = dw[2 * j2], d1 = dw[2 * j2 + 1];
+      double2 qv[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) qv[p] = reinterpret_cast<const double2*>(sq + p * WP)[j2];
+#pragma unroll
+      for (int t = 0; t < WSEP_GT; t++) {
+        const double2 m = reinterpret_cast<const double2*>(row[t])[j2];
+        const double w0 = u0 * m.x, w1 = u1 * m.y;
+        e[t] = fma(w0, m.x, e[t]); e[t] = fma(w1, m.y, e[t]);
+        r0[t] = fma(d0, m.x, r0[t]); r0[t] = fma(d1, m.y, r0[t]);
+#pragma unroll
+        for (int p = 0; p < P; p++) { f[t][p] = fma(w0, qv[p].x, f[t][p]); f[t][p] = fma(w1, qv[p].y, f[t][p]); }
+      }
+    }
+    if (hi & 1) {   // odd end: one more tap (never reads past the window, so a NaN beyond it stays out)
+      const int j = hi - 1;
+      const double u0 = uw[j], d0 = dw[j];
+#pragma unroll
+      for (int t = 0; t < WSEP_GT; t++) {
+        const double m = row[t][j];
+        const double w0 = u0 * m;
+        e[t] = fma(w0, m, e[t]);
+        r0[t] = fma(d0, m, r0[t]);
+#pragma unroll
+        for (int p = 0; p < P; p++) f[t][p] = fma(w0, sq[p * WP + j], f[t][p]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < WSEP_GT; t++) {
+      double s = e[t], r = r0[t];
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        double y = f[t][i];
+#pragma unroll
+        for (int q = 0; q < i; q++) y = fma(-L[i][q], V[t][q], y);
+        y *= inv[i];
+        V[t][i] = y;
+        s = fma(-y, y, s);
+        r = fma(-y, yc[i], r);
+      }
+      V[t][P] = s;
+      V[t][P + 1] = r;
+    }
+  };
+
+  for (int h = 0; h < a.nhyp; h++) {
+    const int glo = a.hyp_begin[h], ghi = a.hyp_begin[h + 1];
+    if (glo >= ghi) continue;
+    const bool half = a.hyp_half[h] != 0;
+    const double hc = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
+    const int nA = a.hyp_nA[h], A0 = a.hyp_A0[h], B0 = a.hyp_B0[h], nB = a.hyp_nB[h];
+    double mx = LSE_EMPTY, sm = 0.0;
+    const int npass = nA > 0 ? (nA + a.arows - 1) / a.arows : 1;
+    for (int pass = 0; pass < npass; pass++) {
+      const int ia0 = pass * a.arows, ia1 = min(nA, ia0 + a.arows);
+      for (int ia = ia0; ia < ia1; ia += WSEP_GT) {
+        double V[WSEP_GT][NV];
+        shape_group(A0 + ia, A0 + ia1 - 1, V);
+#pragma unroll
+        for (int t = 0; t < WSEP_GT; t++) {
+          if (ia + t < ia1) {
+#pragma unroll
+            for (int q = 0; q < NV; q++) ysm[((size_t)(ia + t - ia0) * NV + q) * WSEP_TPB + tid] = V[t][q];
+          }
+        }
+      }
+      int g = glo;
+      for (int ib = 0; ib < nB; ib += WSEP_GT) {
+        double V[WSEP_GT][NV];
+        shape_group(B0 + ib, B0 + nB - 1, V);
+#pragma unroll
+        for (int t = 0; t < WSEP_GT; t++) {
+          const int sb = B0 + ib + t;
+          while (g < ghi && sIdx[2 * g + 1] == sb) {
+            const int ia = sIdx[2 * g];
+            const double kg = sK[g];
+            g++;
+            double s = V[t][P], r = V[t][P + 1];
+            if (nA > 0) {
+              if (ia < ia0 || ia >= ia1) continue;          // another pass owns this template
+              const double* ya = ysm + (size_t)(ia - ia0) * NV * WSEP_TPB + tid;
+              double dot = 0.0;
+#pragma unroll
+              for (int q = 0; q < P; q++) dot = fma(ya[q * WSEP_TPB], V[t][q], dot);
+              s = (s + ya[P * WSEP_TPB]) - 2.0 * dot;
+              r += ya[(P + 1) * WSEP_TPB];
+            }
+            const double w = rsqrt(s);
+            const double z = r * w;
+            double val;
+            if (half) {
+              val = phi_tab(z, sphi);
+              if (z < BFL_PHI_ZFAR) val = phi_half_far(z);
+            } else {
+              val = 0.5 * z * z;
+            }
+            val += kg;
+            if (bad) val = lnBbg - lnBbg;                   // NaN, as (-inf) - (-inf) in the general path
+            lse_push_w(mx, sm, val, w, st64);
+          }
+        }
+      }
+    }
+    a.part[(size_t)h * a.B * nk + ki] = make_double2(mx + hc, sm);
+  }
+}
+
+static size_t wsep_smem(int P, int W, int G, int S, int arows) {
+  const int WP = W + 1;
+  const int nd = (WSEP_TPB + 2 * (W / 2) + 2) & ~1;
+  return sizeof(double) * ((size_t)2 * nd + (size_t)(P + S) * WP + ((G + 1) & ~1) + BFL_PHI_CM_SIZE + 64 +
+                           (size_t)arows * (P + 2) * WSEP_TPB) +
+         sizeof(short) * (size_t)(((2 * G + 7) & ~7) + 2 * S + 8);
+}
+
+// A rows per pass: as many as fit in shared memory, at most the largest hypothesis needs
+static int wsep_arows(const PlanView& pv) {
+  int need = 1;
+  for (int h = 0; h < pv.nhyp; h++) need = std::max(need, pv.hyp_nA[h]);
+  const size_t budget = 220 * 1024;
+  const size_t fixed = wsep_smem(pv.P, pv.W, pv.G, pv.S, 0);
+  if (fixed >= budget) return 0;
+  int fit = (int)((budget - fixed) / (sizeof(double) * (size_t)(pv.P + 2) * WSEP_TPB));
+  fit &= ~(WSEP_GT - 1);
+  return std::min((need + WSEP_GT - 1) & ~(WSEP_GT - 1), fit);
+}
+
+bool wsep_fits(const PlanView& pv) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("BFL_NO_WSEP"); off = (e && atoi(e)) ? 1 : 0; }
+  return !off && pv.wsep_ok && pv.G > 0 && pv.P >= 1 && pv.P <= 6 && wsep_arows(pv) >= WSEP_GT;
+}
+
+cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
+                                   LaunchStats* st) {
+  WsepArgs a;
+  a.dw = sc.dw; a.uu = sc.uu;
+  a.seglen = sv.seglen; a.N = sv.N; a.seg0 = sv.seg0; a.k0 = sv.k0; a.k1 = sv.k1; a.B = sv.B;
+  a.tiles_per_curve = (int)((sv.k1 - sv.k0 + WSEP_TPB - 1) / WSEP_TPB);
+  a.rshapes = pv.rshapes; a.sh_lo = pv.sh_lo; a.sh_hi = pv.sh_hi;
+  a.qb = pv.qb; a.lp = pv.lp; a.lw = pv.lw; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.S = pv.S; a.nhyp = pv.nhyp; a.arows = wsep_arows(pv);
+  for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
+  for (int h = 0; h < pv.nhyp; h++) {
+    a.hyp_half[h] = pv.hyp_half[h];
+    a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; a.hyp_B0[h] = pv.hyp_B0[h]; a.hyp_nB[h] = pv.hyp_nB[h];
+  }
+  a.logdetG = pv.logdetG;
+  a.part = sc.part; a.bgabs = sc.bgabs;
+  const size_t smem = wsep_smem(pv.P, pv.W, pv.G, pv.S, a.arows);
+  dim3 grid((unsigned)(a.tiles_per_curve * a.B));
+  cudaError_t e = cudaSuccess;
+#define BFL_WS(P_)                                                                                              \
+  case P_:                                                                                                      \
+    e = cudaFuncSetAttribute(k_window_wsep<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    if (e != cudaSuccess) return e;                                                                             \
+    k_window_wsep<P_><<<grid, WSEP_TPB, smem, s>>>(a);                                                          \
+    break;
+  switch (pv.P) {
+    BFL_WS(1) BFL_WS(2) BFL_WS(3) BFL_WS(4) BFL_WS(5) BFL_WS(6)
+    default: return cudaErrorInvalidValue;
+  }
+#undef BFL_WS
+  st->launches++;
+  return cudaGetLastError();
 }
 
 // ======================================================================================

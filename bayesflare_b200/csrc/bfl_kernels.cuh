@@ -44,6 +44,14 @@ struct PlanView {
   const short* idxB;         // [G] global shape index
   int hyp_A0[MAXH];          // global shape index of the hypothesis' first A shape
   int hyp_nA[MAXH];          // number of A shapes (0: dense hypothesis)
+  // ---- the same decomposition of the RAW templates, for the weighted path (k_window_wsep): template g =
+  // rshape A (rise) + rshape B (centre + decay) on disjoint supports, so the weighted norm separates too
+  int wsep_ok;
+  const double* rshapes;     // [S][WP]
+  const short* sh_lo;        // [S] first tap of the shape's support (even)
+  const short* sh_hi;        // [S] one past the last tap (<= W)
+  int hyp_B0[MAXH];          // global shape index of the hypothesis' first B shape
+  int hyp_nB[MAXH];          // number of B shapes
 };
 
 constexpr int SEP_MAXA = 16;   // A shapes per hypothesis the kernel keeps per thread in shared memory
@@ -102,6 +110,15 @@ cudaError_t launch_window_general_lse(const PlanView& pv, const SeriesView& sv, 
 cudaError_t launch_window_general_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
                                        bool edges_only, double sumlogsigma, double* d_out,
                                        cudaStream_t s, LaunchStats* st);
+// weighted path: interior samples with per-sample variances, orthonormal-basis form
+bool weighted_fits(const PlanView& pv, const Scratch& sc);
+cudaError_t launch_window_weighted_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
+                                       LaunchStats* st);
+cudaError_t launch_window_weighted_full(const PlanView& pv, int ihyp, const SeriesView& sv, Scratch& sc,
+                                        double sumlogsigma, double* d_out, cudaStream_t s, LaunchStats* st);
+bool wsep_fits(const PlanView& pv);
+cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
+                                   LaunchStats* st);
 // merge partial log-sum-exps, combine hypotheses into log odds
 cudaError_t launch_combine(const PlanView& pv, const SeriesView& sv, const Scratch& sc, int noisepoly,
                            double* d_lnO, double* d_marg, cudaStream_t s, LaunchStats* st);

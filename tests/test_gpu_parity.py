@@ -436,3 +436,83 @@ def test_injection_sweep_driver_config5_small():
     np.testing.assert_array_equal(sum(p["injected"] for p in parts), whole["injected"])
     np.testing.assert_array_equal(sum(p["detected"] for p in parts), whole["detected"])
     assert sum(p["false_alarms"] for p in parts) == whole["false_alarms"]
+
+
+# ---- per-sample variances (real light curves carry PDCSAP_FLUX_ERR): interior samples take the weighted
+# ---- orthonormal-basis kernels (k_window_wsep / k_window_weighted), the edges the reference-order path
+def _varying_cle_case(N, seed):
+    rng = np.random.default_rng(seed)
+    ts = np.arange(N) * DT
+    clc = 1.1 * rng.standard_normal(N) + orc.flare_model(ts, ts[N // 2], 8., 1200., 3900.) \
+        + 1.5 * np.sin(2 * np.pi * ts / (3.1 * 86400.))
+    clc -= np.median(clc)
+    cle = 0.35 + 0.25 * rng.random(N) + 0.1 * np.sin(np.arange(N) / 17.)
+    return ts, clc, cle
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bglen,bgorder", [(55, 4), (55, 2), (55, 5), (55, 0), (35, 3)])
+def test_weighted_detector_vs_oracle(bglen, bgorder):
+    """default detector on a curve with per-sample errors, edges included; bglen 35 has no separable
+    form (the plain weighted kernel runs), bgorder 0..5 instantiate every polynomial size"""
+    ts, clc, cle = _varying_cle_case(900, 100 + bgorder)
+    kw = dict(bglen=bglen, bgorder=bgorder, noiseestmethod="tailveto", ignoreedges=False)
+    if bglen != 55:
+        kw["noiseimpulseparams"] = {"t0": (np.inf,)}
+    det = bf.OddsRatioDetector(_lc(ts, clc, cle), **kw)
+    lnO, _ = det.oddsratio()
+    ref, _ = orc.oddsratio(clc, cle, ts, **kw)
+    assert_logodds_close(lnO, ref, TOL, "weighted W%d o%d" % (bglen, bgorder))
+    np.testing.assert_array_equal(np.nonzero(np.array(lnO) > 10.0)[0], np.nonzero(ref > 10.0)[0])
+
+
+@pytest.mark.gpu
+def test_weighted_dense_grid_multi_pass_and_scripts_detector_vs_oracle():
+    """a 24 x 20 flare grid needs several passes over the rise shapes; the scripts' detector adds a
+    55-point impulse grid (one-tap supports) and reversed decays"""
+    ts, clc, cle = _varying_cle_case(400, 7)
+    fp = {"taugauss": (0, 5400, 24), "tauexp": (1800, 10800, 20)}
+    kw = dict(flareparams=fp, noiseestmethod="tailveto", noiseimpulseparams={"t0": (0, 54 * DT, 55)})
+    det = bf.OddsRatioDetector(_lc(ts, clc, cle), **kw)
+    lnO, _ = det.oddsratio()
+    ref, _ = orc.oddsratio(clc, cle, ts, **kw)
+    assert_logodds_close(lnO, ref, TOL, "weighted dense grid")
+
+
+@pytest.mark.gpu
+def test_weighted_batch_rows_equal_single_curves_and_full_lnB():
+    B, N = 6, 700
+    curves = [_varying_cle_case(N, 200 + b) for b in range(B)]
+    ts = curves[0][0]
+    clc = np.stack([c[1] for c in curves])
+    cle = np.stack([c[2] for c in curves])
+    det = bf.OddsRatioDetector(_lc(ts, clc[0], cle[0]))
+    sk = np.array([det.noise_sigma(_lc(ts, clc[b], cle[b])) for b in range(B)])
+    batch = det.oddsratio_batch(clc, sk=sk, cle=cle)
+    assert batch.shape == (B, N - 54)
+    for b in (0, 3, 5):
+        ref, _ = orc.oddsratio(clc[b], cle[b], ts, sk=float(sk[b]))
+        assert_logodds_close(batch[b], ref, TOL, "weighted batch row %d" % b)
+    # the per-grid-point output (Bayes.lnBmargAmp) takes the plain weighted kernel in full mode
+    pr = {"t0": (np.inf,), "amp": (1.,), "taugauss": (0, 5400, 5), "tauexp": (1800, 10800, 5)}
+    Bf = bf.Bayes(_lc(ts, clc[1], cle[1]), bf.Flare(ts, amp=1, paramranges=pr))
+    Bf.bayes_factors_marg_poly_bgd()
+    s1 = det.noise_sigma(_lc(ts, clc[1], cle[1]))
+    assert det.noiseestmethod == "powerspectrum"
+    ref, _, refbg = orc.bayes_factors(clc[1], cle[1], ts, "flare", pr, s1, with_background=True)
+    assert_logodds_close(Bf.lnBmargAmp, ref, TOL, "weighted full lnB")
+    assert_logodds_close(Bf.bayes_factors_marg_poly_bgd_only(), refbg, TOL, "weighted bg only")
+
+
+@pytest.mark.gpu
+def test_weighted_path_non_finite_samples():
+    """a NaN in the data poisons exactly the windows that contain it (log_marg_amp_full.c:20,25)"""
+    ts, clc, cle = _varying_cle_case(600, 9)
+    clc = clc.copy()
+    clc[300] = np.nan
+    det = bf.OddsRatioDetector(_lc(ts, clc, cle))
+    got = det.plan().detector_odds(clc, cle, 1.0, k0=27, k1=600 - 27)
+    bad = ~np.isfinite(got)
+    expect = np.zeros(600 - 54, dtype=bool)
+    expect[300 - 27 - 27:300 - 27 + 28] = True
+    np.testing.assert_array_equal(bad, expect)
