@@ -361,7 +361,7 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
     CKP(cudaMemcpyAsync((double*)d_raw + (size_t)table_at[i] * WP, table_rows.data() + i * W, sizeof(double) * (size_t)W,
                         cudaMemcpyHostToDevice, s));
   void *d_inorm = nullptr, *d_shapes = nullptr, *d_idxA = nullptr, *d_idxB = nullptr;
-  void *d_rshapes = nullptr, *d_shlo = nullptr, *d_shhi = nullptr;
+  void *d_rshapes = nullptr, *d_shlo = nullptr, *d_shhi = nullptr, *d_shg0 = nullptr, *d_shg1 = nullptr;
   bool wsep_ok = false;
   if ((rc = plan_alloc(p, sizeof(double) * (size_t)std::max(G, 1), &d_inorm))) { bfl_plan_destroy(p); return rc; }
   CKP(launch_plan_orthonormalise((const double*)d_raw, (const double*)d_qb, G, W, WP, P, (double*)d_hat,
@@ -391,7 +391,8 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
                           sizeof(double) * (size_t)WP, cudaMemcpyDeviceToDevice, s));
     // raw-template shapes for the weighted path: A_i = m(tg_i, 0) - m(0, 0) (rise only), B_j = m(0, te_j)
     if ((rc = plan_alloc(p, sizeof(double) * (size_t)S * WP, &d_rshapes)) ||
-        (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shlo)) || (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shhi))) {
+        (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shlo)) || (rc = plan_alloc(p, sizeof(short) * (size_t)S, &d_shhi)) ||
+        (rc = plan_alloc(p, sizeof(int) * (size_t)S, &d_shg0)) || (rc = plan_alloc(p, sizeof(int) * (size_t)S, &d_shg1))) {
       bfl_plan_destroy(p);
       return rc;
     }
@@ -427,6 +428,15 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
               break;
             }
     }
+    // run of templates per B shape (templates of a hypothesis are grouped by B shape, checked above)
+    std::vector<int> sg0(S, 0), sg1(S, 0);
+    for (int g = G - 1; g >= 0; g--) sg0[idxB[g]] = g;
+    for (int g = 0; g < G; g++) sg1[idxB[g]] = g + 1;
+    for (int r = 0; r < S && wsep_ok; r++)
+      for (int g = sg0[r]; g < sg1[r]; g++)
+        if (idxB[g] != r) wsep_ok = false;
+    CKP(cudaMemcpyAsync(d_shg0, sg0.data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, s));
+    CKP(cudaMemcpyAsync(d_shg1, sg1.data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, s));
     CKP(cudaMemcpyAsync(d_shlo, lo.data(), sizeof(short) * (size_t)S, cudaMemcpyHostToDevice, s));
     CKP(cudaMemcpyAsync(d_shhi, hi.data(), sizeof(short) * (size_t)S, cudaMemcpyHostToDevice, s));
     CKP(cudaStreamSynchronize(s));
@@ -438,6 +448,7 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
   pv.idxA = (const short*)d_idxA; pv.idxB = (const short*)d_idxB;
   pv.wsep_ok = (pv.sep_ok && wsep_ok) ? 1 : 0;
   pv.rshapes = (const double*)d_rshapes; pv.sh_lo = (const short*)d_shlo; pv.sh_hi = (const short*)d_shhi;
+  pv.sh_g0 = (const int*)d_shg0; pv.sh_g1 = (const int*)d_shg1;
   pv.raw = (const double*)d_raw; pv.hat = (const double*)d_hat; pv.Kg = (const double*)d_Kg;
   pv.lp = (const double*)d_lp; pv.lw = (const double*)d_lw; pv.gorig = (const int*)d_gorig;
   pv.bg = (const double*)d_bg; pv.bb = (const double*)d_bb; pv.qb = (const double*)d_qb;

@@ -1769,8 +1769,9 @@ struct WsepArgs {
   const double* dw; const double* uu;
   int64_t seglen, N, seg0, k0, k1;
   int B, tiles_per_curve;
-  const double* rshapes; const short* sh_lo; const short* sh_hi;
-  const double* qb; const double* lp; const double* lw; const short* idxA; const short* idxB;
+  int64_t total_tiles;
+  const double* rshapes; const short* sh_lo; const short* sh_hi; const int* sh_g0; const int* sh_g1;
+  const double* qb; const double* lp; const double* lw; const short* idxA;
   int G, W, WP, S, nhyp, arows;
   int hyp_begin[MAXH + 1];
   int hyp_half[MAXH];
@@ -1782,22 +1783,13 @@ struct WsepArgs {
 
 constexpr int WSEP_TPB = 256, WSEP_GT = 4;
 
-// weighted log-sum-exp: s accumulates w_i exp(x_i - m)
-__device__ __forceinline__ void lse_push_w(double& m, double& s, double x, double w, const double* __restrict__ t64) {
-  const double d = x - m;
-  const double e = exp_nonpos(-fabs(d), t64);
-  const bool up = __double2hiint(d) >= 0;
-  s = up ? fma(s, e, w) : fma(w, e, s);
-  m = up ? x : m;
-}
-
+// Persistent CTAs (one per SM): tables staged once, then a static stride over tiles of WSEP_TPB samples.
 template <int P>
 __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
   extern __shared__ double smem[];
   constexpr int NV = P + 2;                        // per shape: y[P], s', r'
   const int W = a.W, H = W / 2, WP = a.WP;
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x % a.tiles_per_curve, b = blockIdx.x / a.tiles_per_curve;
   const int nd = (WSEP_TPB + 2 * H + 2) & ~1;
   double* su = smem;                               // [nd] 1/v
   double* sud = su + nd;                           // [nd] d/v
@@ -1807,10 +1799,30 @@ __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
   double* sphi = sK + ((a.G + 1) & ~1);            // [(DEG+1) * NI]
   double* st64 = sphi + BFL_PHI_CM_SIZE;           // [64]
   double* ysm = st64 + 64;                         // [arows][NV][TPB]
-  short* sIdx = reinterpret_cast<short*>(ysm + (size_t)a.arows * NV * WSEP_TPB);   // [G][2]
-  short* sLoHi = sIdx + ((2 * a.G + 7) & ~7);      // [S][2]
+  int* sG01 = reinterpret_cast<int*>(ysm + (size_t)a.arows * NV * WSEP_TPB);   // [S][2] templates using shape s as B
+  short* sIdxA = reinterpret_cast<short*>(sG01 + 2 * a.S);                     // [G]
+  short* sLoHi = sIdxA + ((a.G + 7) & ~7);                                     // [S][2]
 
+  for (int i = tid; i < P * WP; i += WSEP_TPB) sq[i] = a.qb[i];
+  for (int i = tid; i < a.S * WP; i += WSEP_TPB) ssh[i] = a.rshapes[i];
+  for (int i = tid; i < a.G; i += WSEP_TPB) { sK[i] = a.lp[i] + a.lw[i]; sIdxA[i] = a.idxA[i]; }
+  for (int i = tid; i < a.S; i += WSEP_TPB) {
+    sLoHi[2 * i] = a.sh_lo[i]; sLoHi[2 * i + 1] = a.sh_hi[i];
+    sG01[2 * i] = a.sh_g0[i]; sG01[2 * i + 1] = a.sh_g1[i];
+  }
+  if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
+  for (int i = tid; i < BFL_PHI_CM_SIZE; i += WSEP_TPB) {
+    const int cidx = i / BFL_PHI_NI, kk = i - cidx * BFL_PHI_NI;
+    sphi[i] = BFL_PHI_TAB[kk * BFL_PHI_ROW + cidx];
+  }
+  const int64_t nk = a.k1 - a.k0;
+  const double* uw = su + tid;
+  const double* dw = sud + tid;
+
+  for (int64_t tl = blockIdx.x; tl < a.total_tiles; tl += gridDim.x) {
+  const int tile = (int)(tl % a.tiles_per_curve), b = (int)(tl / a.tiles_per_curve);
   const int64_t kbase = a.k0 + (int64_t)tile * WSEP_TPB;
+  __syncthreads();                                 // the previous tile is done with su / sud
   {
     const double* du = a.uu + (size_t)b * a.seglen;
     const double* dd = a.dw + (size_t)b * a.seglen;
@@ -1821,27 +1833,11 @@ __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
       su[i] = in ? 1.0 / du[sidx - a.seg0] : 0.0;
       sud[i] = in ? dd[sidx - a.seg0] : 0.0;
     }
-    for (int i = tid; i < P * WP; i += WSEP_TPB) sq[i] = a.qb[i];
-    for (int i = tid; i < a.S * WP; i += WSEP_TPB) ssh[i] = a.rshapes[i];
-    for (int i = tid; i < a.G; i += WSEP_TPB) {
-      sK[i] = a.lp[i] + a.lw[i];
-      sIdx[2 * i] = a.idxA[i];
-      sIdx[2 * i + 1] = a.idxB[i];
-    }
-    for (int i = tid; i < a.S; i += WSEP_TPB) { sLoHi[2 * i] = a.sh_lo[i]; sLoHi[2 * i + 1] = a.sh_hi[i]; }
-    if (tid < 64) st64[tid] = exp2((double)tid * (1.0 / 64.0));
-    for (int i = tid; i < BFL_PHI_CM_SIZE; i += WSEP_TPB) {
-      const int cidx = i / BFL_PHI_NI, kk = i - cidx * BFL_PHI_NI;
-      sphi[i] = BFL_PHI_TAB[kk * BFL_PHI_ROW + cidx];
-    }
   }
   __syncthreads();
   const int64_t k = kbase + tid;
-  if (k >= a.k1 || k < H || k >= a.N - H) return;      // interior samples only
-  const int64_t nk = a.k1 - a.k0;
+  if (k >= a.k1 || k < H || k >= a.N - H) continue;    // interior samples only (no barrier below this line)
   const int64_t ki = (int64_t)b * nk + (k - a.k0);
-  const double* uw = su + tid;
-  const double* dw = sud + tid;
 
   // ---- A = Q U Q^T = L L^T, yc = L^-1 Q U d ----
   double L[P][P], inv[P], yc[P];
@@ -1891,7 +1887,7 @@ __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
     }
   }
   double lnBbg = -0.5 * a.logdetG - 0.5 * logdetA + 0.5 * quad + 0.5 * P * (BFL_LN2 + BFL_LNPI);
-  const bool bad = !isfinite(lnBbg);
+  const bool bad = !isfinite(lnBbg);               // non-finite data or variances, log_marg_amp_full.c:20,25
   if (bad) lnBbg = neg_inf();
   if (a.bgabs) a.bgabs[ki] = lnBbg;
 
@@ -1960,12 +1956,38 @@ __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
   };
 
   for (int h = 0; h < a.nhyp; h++) {
-    const int glo = a.hyp_begin[h], ghi = a.hyp_begin[h + 1];
-    if (glo >= ghi) continue;
+    if (a.hyp_begin[h] >= a.hyp_begin[h + 1]) continue;
     const bool half = a.hyp_half[h] != 0;
     const double hc = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
     const int nA = a.hyp_nA[h], A0 = a.hyp_A0[h], B0 = a.hyp_B0[h], nB = a.hyp_nB[h];
     double mx = LSE_EMPTY, sm = 0.0;
+    // WSEP_GT templates at a time: independent chains through rsqrt, phi and exp, one merge into (mx, sm)
+    auto term = [&](double s, double r, double kg, bool valid, double& x, double& w) {
+      w = rsqrt(s);
+      const double z = r * w;
+      double val;
+      if (half) {
+        val = phi_tab(z, sphi);
+        if (z < BFL_PHI_ZFAR) val = phi_half_far(z);
+      } else {
+        val = 0.5 * z * z;
+      }
+      x = valid ? val + kg : LSE_EMPTY;
+      w = valid ? w : 0.0;
+    };
+    auto merge = [&](const double (&x)[WSEP_GT], const double (&w)[WSEP_GT]) {
+      double bm = x[0];
+#pragma unroll
+      for (int c = 1; c < WSEP_GT; c++) bm = fmax(bm, x[c]);
+      double bs = 0.0;
+#pragma unroll
+      for (int c = 0; c < WSEP_GT; c++) bs = fma(w[c], exp_nonpos(x[c] - bm, st64), bs);
+      const double d = bm - mx;
+      const double e = exp_nonpos(-fabs(d), st64);
+      const bool up = __double2hiint(d) >= 0;
+      sm = up ? fma(sm, e, bs) : fma(bs, e, sm);
+      mx = up ? bm : mx;
+    };
     const int npass = nA > 0 ? (nA + a.arows - 1) / a.arows : 1;
     for (int pass = 0; pass < npass; pass++) {
       const int ia0 = pass * a.arows, ia1 = min(nA, ia0 + a.arows);
@@ -1980,45 +2002,50 @@ __global__ void __launch_bounds__(WSEP_TPB) k_window_wsep(const WsepArgs a) {
           }
         }
       }
-      int g = glo;
       for (int ib = 0; ib < nB; ib += WSEP_GT) {
         double V[WSEP_GT][NV];
         shape_group(B0 + ib, B0 + nB - 1, V);
+        if (nA > 0) {
+          // separable hypothesis: every B shape pairs with a run of templates (one per admissible A)
 #pragma unroll
-        for (int t = 0; t < WSEP_GT; t++) {
-          const int sb = B0 + ib + t;
-          while (g < ghi && sIdx[2 * g + 1] == sb) {
-            const int ia = sIdx[2 * g];
-            const double kg = sK[g];
-            g++;
-            double s = V[t][P], r = V[t][P + 1];
-            if (nA > 0) {
-              if (ia < ia0 || ia >= ia1) continue;          // another pass owns this template
-              const double* ya = ysm + (size_t)(ia - ia0) * NV * WSEP_TPB + tid;
-              double dot = 0.0;
+          for (int t = 0; t < WSEP_GT; t++) {
+            if (ib + t >= nB) break;
+            const int g0 = sG01[2 * (B0 + ib + t)], g1 = sG01[2 * (B0 + ib + t) + 1];
+            for (int g = g0; g < g1; g += WSEP_GT) {
+              double x[WSEP_GT], w[WSEP_GT];
 #pragma unroll
-              for (int q = 0; q < P; q++) dot = fma(ya[q * WSEP_TPB], V[t][q], dot);
-              s = (s + ya[P * WSEP_TPB]) - 2.0 * dot;
-              r += ya[(P + 1) * WSEP_TPB];
+              for (int c = 0; c < WSEP_GT; c++) {
+                const int gi = min(g + c, g1 - 1);
+                const int ia = sIdxA[gi];
+                const bool valid = (g + c < g1) && ia >= ia0 && ia < ia1;
+                const double* ya = ysm + (size_t)min(max(ia - ia0, 0), a.arows - 1) * NV * WSEP_TPB + tid;
+                double dot = 0.0;
+#pragma unroll
+                for (int q = 0; q < P; q++) dot = fma(ya[q * WSEP_TPB], V[t][q], dot);
+                const double s = (V[t][P] + ya[P * WSEP_TPB]) - 2.0 * dot;
+                const double r = V[t][P + 1] + ya[(P + 1) * WSEP_TPB];
+                term(s, r, sK[gi], valid, x[c], w[c]);
+              }
+              merge(x, w);
             }
-            const double w = rsqrt(s);
-            const double z = r * w;
-            double val;
-            if (half) {
-              val = phi_tab(z, sphi);
-              if (z < BFL_PHI_ZFAR) val = phi_half_far(z);
-            } else {
-              val = 0.5 * z * z;
-            }
-            val += kg;
-            if (bad) val = lnBbg - lnBbg;                   // NaN, as (-inf) - (-inf) in the general path
-            lse_push_w(mx, sm, val, w, st64);
           }
+        } else {
+          // dense hypothesis: one template per shape, the group is the batch
+          double x[WSEP_GT], w[WSEP_GT];
+#pragma unroll
+          for (int t = 0; t < WSEP_GT; t++) {
+            const int sb = min(B0 + ib + t, B0 + nB - 1);
+            const int gi = sG01[2 * sb];
+            term(V[t][P], V[t][P + 1], sK[gi], ib + t < nB && sG01[2 * sb + 1] > gi, x[t], w[t]);
+          }
+          merge(x, w);
         }
       }
     }
+    if (bad) { mx = lnBbg - lnBbg; sm = mx; }      // NaN, as (-inf) - (-inf) in the general path
     a.part[(size_t)h * a.B * nk + ki] = make_double2(mx + hc, sm);
   }
+  }   // tile loop
 }
 
 static size_t wsep_smem(int P, int W, int G, int S, int arows) {
@@ -2026,7 +2053,7 @@ static size_t wsep_smem(int P, int W, int G, int S, int arows) {
   const int nd = (WSEP_TPB + 2 * (W / 2) + 2) & ~1;
   return sizeof(double) * ((size_t)2 * nd + (size_t)(P + S) * WP + ((G + 1) & ~1) + BFL_PHI_CM_SIZE + 64 +
                            (size_t)arows * (P + 2) * WSEP_TPB) +
-         sizeof(short) * (size_t)(((2 * G + 7) & ~7) + 2 * S + 8);
+         sizeof(int) * (size_t)(2 * S) + sizeof(short) * (size_t)(((G + 7) & ~7) + 2 * S + 8);
 }
 
 // A rows per pass: as many as fit in shared memory, at most the largest hypothesis needs
@@ -2053,8 +2080,9 @@ cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scr
   a.dw = sc.dw; a.uu = sc.uu;
   a.seglen = sv.seglen; a.N = sv.N; a.seg0 = sv.seg0; a.k0 = sv.k0; a.k1 = sv.k1; a.B = sv.B;
   a.tiles_per_curve = (int)((sv.k1 - sv.k0 + WSEP_TPB - 1) / WSEP_TPB);
-  a.rshapes = pv.rshapes; a.sh_lo = pv.sh_lo; a.sh_hi = pv.sh_hi;
-  a.qb = pv.qb; a.lp = pv.lp; a.lw = pv.lw; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.total_tiles = (int64_t)a.tiles_per_curve * sv.B;
+  a.rshapes = pv.rshapes; a.sh_lo = pv.sh_lo; a.sh_hi = pv.sh_hi; a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1;
+  a.qb = pv.qb; a.lp = pv.lp; a.lw = pv.lw; a.idxA = pv.idxA;
   a.G = pv.G; a.W = pv.W; a.WP = pv.WP; a.S = pv.S; a.nhyp = pv.nhyp; a.arows = wsep_arows(pv);
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   for (int h = 0; h < pv.nhyp; h++) {
@@ -2064,7 +2092,13 @@ cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scr
   a.logdetG = pv.logdetG;
   a.part = sc.part; a.bgabs = sc.bgabs;
   const size_t smem = wsep_smem(pv.P, pv.W, pv.G, pv.S, a.arows);
-  dim3 grid((unsigned)(a.tiles_per_curve * a.B));
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  dim3 grid((unsigned)std::min<int64_t>(a.total_tiles, sms));   // persistent: one CTA per SM (shared-memory bound)
   cudaError_t e = cudaSuccess;
 #define BFL_WS(P_)                                                                                              \
   case P_:                                                                                                      \

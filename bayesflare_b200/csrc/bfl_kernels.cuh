@@ -50,6 +50,8 @@ struct PlanView {
   const double* rshapes;     // [S][WP]
   const short* sh_lo;        // [S] first tap of the shape's support (even)
   const short* sh_hi;        // [S] one past the last tap (<= W)
+  const int* sh_g0;          // [S] templates [sh_g0, sh_g1) use shape s as their B shape (empty for A shapes)
+  const int* sh_g1;
   int hyp_B0[MAXH];          // global shape index of the hypothesis' first B shape
   int hyp_nB[MAXH];          // number of B shapes
 };
