@@ -15,9 +15,12 @@ from .noise import estimate_noise_ps, estimate_noise_tv, savitzky_golay, nextpow
 from .general import logplus, logminus, logtrapz
 from .bayes import Bayes, ParameterEstimationGrid
 from .finder import OddsRatioDetector, contiguous_regions
+from .search import flare_search, merge_results, write_result
+from . import fitsio
 
 __version__ = "0.1.0"
 
 __all__ = ["Lightcurve", "Model", "Flare", "Transit", "Expdecay", "Impulse", "Gaussian", "Step", "ModelCurve",
            "estimate_noise_ps", "estimate_noise_tv", "savitzky_golay", "nextpow2", "logplus", "logminus",
-           "logtrapz", "Bayes", "ParameterEstimationGrid", "OddsRatioDetector", "contiguous_regions"]
+           "logtrapz", "Bayes", "ParameterEstimationGrid", "OddsRatioDetector", "contiguous_regions",
+           "flare_search", "merge_results", "write_result", "fitsio"]

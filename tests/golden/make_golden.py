@@ -277,9 +277,51 @@ def gold_pe(bf):
     save("pegrid", **out)
 
 
+def gold_ingest(bf):
+    """Ingest conditioning + Kepler-search detector on a file-like light curve (float32 flux with NaN
+    gaps, per-sample float32 errors): data.py:240-277, 279-351; scripts/kepler_analysis_script.py:376-382.
+    The FITS container itself is not exercised by the reference here (no pyfits/astropy in the image):
+    the arrays a file would deliver are appended exactly as ``add_data`` appends them."""
+    rng = np.random.RandomState(77)
+    N = 700
+    time_days = 131.5 + np.arange(N) * (DT_LONG / 86400.)
+    ts = time_days * 24 * 3600
+    flux = 12000. + 8. * rng.randn(N) + 30. * np.sin(2 * np.pi * np.arange(N) / 310.)
+    flux += ref_flare(bf, ts, ts[400], 160., 900., 4200.) + ref_flare(bf, ts, ts[150], 110., 1500., 6000.)
+    err = 8. + 0.6 * np.sin(np.arange(N) / 40.) + 0.3 * rng.rand(N)
+    flux32, err32 = flux.astype(np.float32), err.astype(np.float32)
+    for a, b in ((60, 61), (233, 235), (520, 523)):
+        flux32[a:b] = np.nan
+        err32[a:b] = np.nan
+    lc = bf.Lightcurve()
+    lc.clc = np.append(np.array([]), flux32.copy())
+    lc.cts = np.append(np.array([]), time_days * 24 * 3600)
+    lc.cle = np.append(np.array([]), err32.copy())
+    out = {"time_days": time_days, "flux32": flux32, "err32": err32}
+    out["ref_datagap"] = np.array(lc.gap_checker(lc.clc, maxgap=2))
+    lc.interpolate()
+    lc.dcoffset()
+    out["ref_clc"], out["ref_cts"], out["ref_cle"], out["ref_dc"] = lc.clc.copy(), lc.cts.copy(), lc.cle.copy(), np.array(lc.dc)
+    odds = bf.OddsRatioDetector(lc, noiseestmethod='tailveto', tvsigma=1.0)
+    odds.set_noise_impulse(noiseimpulseparams={'t0': (0, (odds.bglen - 1.) * lc.dt(), odds.bglen)})
+    lnO, tso = odds.oddsratio()
+    out["ref_lnO"] = np.array(lnO)
+    segs, n, mx = odds.thresholder(lnO, 16.5, expand=1)
+    out["ref_segs"] = np.array(segs, dtype=np.int64).reshape(-1, 2)
+    out["ref_max"] = np.array(mx, dtype=float).reshape(-1, 2)
+    import copy
+    tmp = copy.copy(lc)
+    tmp.detrend(method='savitzkygolay', nbins=odds.bglen, order=odds.bgorder)
+    out["ref_sk"] = np.array(bf.estimate_noise_tv(tmp.clc, sigma=odds.tvsigma)[0])
+    save("ingest", **out)
+    print("   ingest: %d segments, nan lnO %d, max %.3f" % (n, int(np.isnan(out["ref_lnO"]).sum()), np.nanmax(out["ref_lnO"])))
+
+
 def main():
     bf = ref_loader.load_reference()
-    which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid"]
+    which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid", "ingest"]
+    if "ingest" in which:
+        gold_ingest(bf)
     if "scalars" in which:
         gold_scalars(bf)
     if "elimination" in which:

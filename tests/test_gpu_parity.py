@@ -516,3 +516,40 @@ def test_weighted_path_non_finite_samples():
     expect = np.zeros(600 - 54, dtype=bool)
     expect[300 - 27 - 27:300 - 27 + 28] = True
     np.testing.assert_array_equal(bad, expect)
+
+
+@pytest.mark.gpu
+def test_kepler_search_from_fits_files_vs_reference(tmp_path):
+    """SURVEY 8(f) f4 end to end: FITS files -> Lightcurve conditioning -> batched device search -> the
+    script's JSON record, against the reference's own detector output on the same file content."""
+    from bayesflare_b200 import fitsio
+    g = load_golden("ingest")
+    paths = []
+    for i, kid in enumerate((1001, 1002, 1003)):
+        p = str(tmp_path / ("kplr%09d_llc.fits" % kid))
+        flux = g["flux32"].copy()
+        if i == 2:
+            flux = np.float32(12000.) + (flux - np.float32(12000.)) * np.float32(0.02)    # a quiet star
+        fitsio.write_lightcurve(p, g["time_days"], flux, g["err32"], kepid=kid, quarter=1)
+        paths.append(p)
+    lc = bf.Lightcurve(curve=paths[0], maxgap=2)
+    det = bf.OddsRatioDetector(lc, noiseestmethod='tailveto', tvsigma=1.0)
+    det.set_noise_impulse(noiseimpulseparams={'t0': (0, (det.bglen - 1.) * lc.dt(), det.bglen)})
+    lnO, ts = det.oddsratio()
+    assert_logodds_close(lnO, g["ref_lnO"], TOL, "ingested curve")       # identical NaN pattern around the gaps
+    out = bf.flare_search(paths, threshold=16.5, expand=1, star_info={1001: {"teff": 4000, "logg": 4.5}})
+    assert out["No. stars analysed"] == 3 and out["Star list"] == [1001, 1002, 1003]
+    assert out["Flaring stars"] == [1001, 1002] and out["No. flares"] == 2 * len(g["ref_segs"])
+    assert out["Running window length"] == 55 and out["Noise estimation method"] == "tailveto"
+    rec = out["Flaring star data"]["KPLR000001001"]
+    assert rec["Max. indices"] == [int(i) for i in g["ref_max"][:, 1]] and rec["Teff"] == 4000
+    np.testing.assert_allclose(rec["Max. odds ratios"], g["ref_max"][:, 0], rtol=1e-9)
+    assert [s[0] for s in rec["Segment indices"]] == [int(a) for a in g["ref_segs"][:, 0]]
+    assert [s[-1] + 1 for s in rec["Segment indices"]] == [int(b) for b in g["ref_segs"][:, 1]]
+    assert abs(rec["Noise sigma"] - float(g["ref_sk"])) <= 1e-9 * float(g["ref_sk"])
+    assert rec["Lightcurve DC background"] == float(g["ref_dc"])
+    np.testing.assert_allclose(rec["Max. times"], [g["ref_cts"][27:-27][int(i)] for i in g["ref_max"][:, 1]])
+    bf.write_result(out, str(tmp_path / "res.json"))
+    # restart: already analysed stars are skipped
+    again = bf.flare_search(paths, threshold=16.5, outdict=out)
+    assert again["No. stars analysed"] == 3
