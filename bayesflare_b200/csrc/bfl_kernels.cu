@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <type_traits>
 
 namespace bfl {
 
@@ -97,6 +98,33 @@ __device__ __forceinline__ double phi_tab_rows(double z, const double* __restric
 }
 __device__ __noinline__ double phi_half_far(double z) {   // z < -12.06: log erfcx(-z/sqrt2)
   return log(erfcx(-z * 0.70710678118654752440));
+}
+
+#include "exphi_table.inc"
+// E(z) = exp(phi(z)) for |z| <= BFL_EXPHI_ZC (tools/gen_exphi_table.py, relative error < 2e-12).
+// The look-up is lane-varying and shared-memory wavefronts bound the epilogue, so a row is ONE 16-byte
+// load (E_k, g_k = sqrt(2/pi)/E_k); the derivatives of phi at the node follow from dg/dz = -g dphi/dz and
+// the rest is arithmetic: t = phi(z) - phi(z_k) to third order in d = z - z_k (|d| <= 1/256), E = E_k e^t
+// with a degree-5 series (|t| < 0.025).  The caller checks |z| <= ZC; the index is clamped so an
+// out-of-range z reads a valid row (its value is discarded).
+#define BFL_EXPHI_SIZE (2 * BFL_EXPHI_NI)
+__device__ __forceinline__ double exphi_eval(double z, const double* __restrict__ tab) {
+  const double s = fma(z, BFL_EXPHI_INVH, BFL_EXPHI_ZC * BFL_EXPHI_INVH);
+  int k = __double2int_rn(s);
+  k = min(max(k, 0), BFL_EXPHI_NI - 1);
+  const double d = (s - (double)k) * (1.0 / BFL_EXPHI_INVH);
+  const double2 eg = reinterpret_cast<const double2*>(tab)[k];
+  const double g = eg.y;
+  const double p1 = (z - d) + g;                 // first derivative of phi at z_k
+  const double p2 = fma(-g, p1, 1.0);            // second
+  const double p3 = g * fma(p1, p1, -p2);        // third
+  const double t = d * fma(d, fma(d, p3 * (1.0 / 6.0), 0.5 * p2), p1);
+  double e = fma(t, 1.0 / 120.0, 1.0 / 24.0);
+  e = fma(e, t, 1.0 / 6.0);
+  e = fma(e, t, 0.5);
+  e = fma(e, t, 1.0);
+  e = fma(e, t, 1.0);
+  return eg.x * e;
 }
 
 // e^d for d <= 0 (NaN propagates), two variants:
@@ -765,23 +793,47 @@ struct EpiArgs {
 
 constexpr int EPI_TPB = 256;
 
+// Two evaluation strategies per thread tile:
+//  * LINEAR (first): nearly every sample is noise, where every |z_g| is a few units.  Then the grid sum
+//    is accumulated directly, S_h = sum_g c_g E(z_g) with c_g = exp(K_g + lp_g + lw_g - Cref_h) fixed per
+//    plan and E = exp(phi) from exphi_eval (one 16-byte look-up + ~20 FMAs per template) -- no exp range reduction, no
+//    running maximum.  Full-range templates use exp(z^2/2 - ZC^2/2) (one exp, no maximum).
+//  * LOG (fallback, only for threads that met a |z| > ZC, i.e. a flare or a deep dip): phi table +
+//    online log-sum-exp, any z.  Its phi table is read from global memory (L1): it is rarely needed and
+//    shared memory is better spent on occupancy.
+// Both produce (reference value, sum) pairs per hypothesis, folded into the odds the same way.
 template <int MODE, int SPT>
 __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int G = a.G;
   double* sK = smem;                                     // [G] Kg + lp + lw
-  double* sInorm = sK + ((G + 1) & ~1);                  // [G]
-  double* sphi = sInorm + ((G + 1) & ~1);                // phi table
-  short* sIdx = reinterpret_cast<short*>(sphi + BFL_PHI_STRIDE);   // [G][2]
+  double* sC = sK + ((G + 1) & ~1);                      // [G] exp(sK - Cref_h)
+  double* sInorm = sC + ((G + 1) & ~1);                  // [G]
+  double* sCref = sInorm + ((G + 1) & ~1);               // [MAXH]
+  double* sE = sCref + MAXH;                             // E(z) table
+  short* sIdx = reinterpret_cast<short*>(sE + BFL_EXPHI_SIZE);   // [G][2]
   for (int i = tid; i < G; i += EPI_TPB) {
     sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
     sInorm[i] = a.inorm[i];
     sIdx[2 * i] = a.idxA[i];
     sIdx[2 * i + 1] = a.idxB[i];
   }
-  for (int i = tid; i < BFL_PHI_STRIDE; i += EPI_TPB) sphi[i] = BFL_PHI_TAB[i];
+  for (int i = tid; i < BFL_EXPHI_SIZE; i += EPI_TPB) sE[i] = BFL_EXPHI_TAB[i];
   __syncthreads();
+  if (tid < a.nhyp) {
+    double m = -1.0e300;
+    for (int g = a.hyp_begin[tid]; g < a.hyp_begin[tid + 1]; g++) m = fmax(m, sK[g]);
+    sCref[tid] = m;
+  }
+  __syncthreads();
+  for (int i = tid; i < G; i += EPI_TPB) {
+    int h = 0;
+    while (a.hyp_begin[h + 1] <= i) h++;
+    sC[i] = exp(sK[i] - sCref[h]);
+  }
+  __syncthreads();
+  constexpr double ZC = BFL_EXPHI_ZC;
 
   const int64_t tile_samples = (int64_t)EPI_TPB * SPT;
   const int64_t ntiles = (a.BK + tile_samples - 1) / tile_samples;
@@ -799,79 +851,107 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
       valid[j] = valid[j] && (k >= a.H) && (k < a.N - a.H);   // interior samples only
       hlv[j] = a.halflogv[b];
     }
-    double mx[SPT], sm[SPT], n_m[SPT], n_s[SPT], d_m[SPT], d_s[SPT];
-#pragma unroll
-    for (int j = 0; j < SPT; j++) {
-      mx[j] = LSE_EMPTY; sm[j] = 0.0;
-      n_m[j] = LSE_EMPTY; n_s[j] = 0.0;
-      d_m[j] = a.noisepoly ? 0.0 : LSE_EMPTY; d_s[j] = a.noisepoly ? 1.0 : 0.0;
-    }
-    for (int h = 0; h < a.nhyp; h++) {
-      const int glo = a.hyp_begin[h], ghi = a.hyp_begin[h + 1];
-      if (glo >= ghi) continue;
-      const bool half = a.hyp_half[h] != 0;
-      {
-        // the A-shape correlations of a template are re-read through L1 (each is shared by the
-        // templates of one rise time); the B-shape value stays in registers while it is shared
-        const double* YA = a.Y + (size_t)a.hyp_A0[h] * a.BK;
-        int curB = -1;
-        double yB[SPT];
-        for (int g = glo; g < ghi; g++) {
-          const int ia = sIdx[2 * g], ib = sIdx[2 * g + 1];
-          if (ib != curB) {
-            curB = ib;
-#pragma unroll
-            for (int j = 0; j < SPT; j++) yB[j] = __ldg(a.Y + (size_t)ib * a.BK + idx[j]);
-          }
-          const double kg = sK[g];
-          const double sc = (ia >= 0) ? sInorm[g] : 1.0;
-          double z[SPT], val[SPT];
-#pragma unroll
-          for (int j = 0; j < SPT; j++)
-            z[j] = (ia >= 0) ? sc * (__ldg(YA + (size_t)ia * a.BK + idx[j]) + yB[j]) : yB[j];
-          if (half) {
-            bool far_ = false;
-#pragma unroll
-            for (int j = 0; j < SPT; j++) {
-              val[j] = kg + phi_tab_rows(z[j], sphi);
-              far_ = far_ || (z[j] < BFL_PHI_ZFAR);
-            }
-            if (far_) {
-#pragma unroll
-              for (int j = 0; j < SPT; j++)
-                if (z[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(z[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
-          }
-#pragma unroll
-          for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
-        }
-      }
-      // hypothesis finished: partial out (MODE 0) or fold into numerator / denominator (MODE 2)
-      const double hcb = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
+    double lnO[SPT];
+    bool big = false;
+
+    auto body = [&](auto LIN) {
+      constexpr bool lin = decltype(LIN)::value;
+      double mx[SPT], sm[SPT], n_m[SPT], n_s[SPT], d_m[SPT], d_s[SPT];
 #pragma unroll
       for (int j = 0; j < SPT; j++) {
-        const double x = mx[j] + (hcb + hlv[j]);
-        if (MODE == 0) {
-          if (valid[j]) a.part[(size_t)h * a.BK + idx[j]] = make_double2(x, sm[j]);
-        } else if (h == 0) {
-          n_m[j] = x; n_s[j] = sm[j];
-        } else {
-          const double d = x - d_m[j];
-          const double e = exp_nonpos_poly(-fabs(d));
-          const bool up = d > 0.0;
-          d_s[j] = up ? fma(d_s[j], e, sm[j]) : fma(sm[j], e, d_s[j]);
-          d_m[j] = up ? x : d_m[j];
-        }
         mx[j] = LSE_EMPTY; sm[j] = 0.0;
+        n_m[j] = LSE_EMPTY; n_s[j] = 0.0;
+        d_m[j] = a.noisepoly ? 0.0 : LSE_EMPTY; d_s[j] = a.noisepoly ? 1.0 : 0.0;
       }
-    }
+      for (int h = 0; h < a.nhyp; h++) {
+        const int glo = a.hyp_begin[h], ghi = a.hyp_begin[h + 1];
+        if (glo >= ghi) continue;
+        const bool half = a.hyp_half[h] != 0;
+        {
+          // the A-shape correlations of a template are re-read through L1 (each is shared by the
+          // templates of one rise time); the B-shape value stays in registers while it is shared
+          const double* YA = a.Y + (size_t)a.hyp_A0[h] * a.BK;
+          int curB = -1;
+          double yB[SPT];
+          for (int g = glo; g < ghi; g++) {
+            const int ia = sIdx[2 * g], ib = sIdx[2 * g + 1];
+            if (ib != curB) {
+              curB = ib;
+#pragma unroll
+              for (int j = 0; j < SPT; j++) yB[j] = __ldg(a.Y + (size_t)ib * a.BK + idx[j]);
+            }
+            const double sc = (ia >= 0) ? sInorm[g] : 1.0;
+            double z[SPT];
+#pragma unroll
+            for (int j = 0; j < SPT; j++)
+              z[j] = (ia >= 0) ? sc * (__ldg(YA + (size_t)ia * a.BK + idx[j]) + yB[j]) : yB[j];
+            if constexpr (lin) {
+              const double cg = sC[g];
+#pragma unroll
+              for (int j = 0; j < SPT; j++) {
+                big = big || (fabs(z[j]) > ZC);
+                const double e = half ? exphi_eval(z[j], sE) : exp_nonpos_poly(fma(0.5 * z[j], z[j], -0.5 * ZC * ZC));
+                sm[j] = fma(cg, e, sm[j]);
+              }
+            } else {
+              const double kg = sK[g];
+              double val[SPT];
+              if (half) {
+                bool far_ = false;
+#pragma unroll
+                for (int j = 0; j < SPT; j++) {
+                  val[j] = kg + phi_tab_rows(z[j], BFL_PHI_TAB);
+                  far_ = far_ || (z[j] < BFL_PHI_ZFAR);
+                }
+                if (far_) {
+#pragma unroll
+                  for (int j = 0; j < SPT; j++)
+                    if (z[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(z[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
+              }
+#pragma unroll
+              for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
+            }
+          }
+        }
+        // hypothesis finished: partial out (MODE 0) or fold into numerator / denominator (MODE 2)
+        const double hcb = half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI);
+        if constexpr (lin) {
+          const double ref = sCref[h] + (half ? 0.0 : 0.5 * ZC * ZC);
+#pragma unroll
+          for (int j = 0; j < SPT; j++) mx[j] = ref;
+        }
+#pragma unroll
+        for (int j = 0; j < SPT; j++) {
+          const double x = mx[j] + (hcb + hlv[j]);
+          if (MODE == 0) {
+            if (valid[j]) a.part[(size_t)h * a.BK + idx[j]] = make_double2(x, sm[j]);
+          } else if (h == 0) {
+            n_m[j] = x; n_s[j] = sm[j];
+          } else {
+            const double d = x - d_m[j];
+            const double e = exp_nonpos_poly(-fabs(d));
+            const bool up = d > 0.0;
+            d_s[j] = up ? fma(d_s[j], e, sm[j]) : fma(sm[j], e, d_s[j]);
+            d_m[j] = up ? x : d_m[j];
+          }
+          mx[j] = LSE_EMPTY; sm[j] = 0.0;
+        }
+      }
+      if (MODE == 2) {
+#pragma unroll
+        for (int j = 0; j < SPT; j++) lnO[j] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
+      }
+    };
+    body(std::true_type{});
+    if (big) body(std::false_type{});
     if (MODE == 2) {
 #pragma unroll
       for (int j = 0; j < SPT; j++)
-        if (valid[j]) a.lnO[idx[j]] = (n_m[j] - d_m[j]) + log(n_s[j] / d_s[j]);
+        if (valid[j]) a.lnO[idx[j]] = lnO[j];
     }
   }
 }
@@ -882,7 +962,7 @@ static size_t corr_smem_bytes(int S, int KT) {
 }
 static size_t epi_smem_bytes(int G, int SPT) {
   (void)SPT;
-  return sizeof(double) * (size_t)(2 * ((G + 1) & ~1) + BFL_PHI_STRIDE) + sizeof(short) * (size_t)(2 * G + 8);
+  return sizeof(double) * (size_t)(3 * ((G + 1) & ~1) + MAXH + BFL_EXPHI_SIZE) + sizeof(short) * (size_t)(2 * G + 8);
 }
 
 bool fast_split_fits(const PlanView& pv) {

@@ -219,9 +219,34 @@ def config5(nreal=10000):
             "transit_odds_s": t_tr, "transit_parity_max_scaled_err": scaled_err(B.lnBmargAmp, reft)}
 
 
+def config6(B=512):
+    """extra (not a BASELINE config): batch of long-cadence curves WITH per-sample errors, as real Kepler files
+    carry (PDCSAP_FLUX_ERR) -- the weighted kernels; device noise estimate, host buffers in and out"""
+    N = 4400
+    cts, clc, _ = simulate_batch(B, N, seed=66)
+    rng = np.random.default_rng(6)
+    cle = 0.3 + 0.2 * rng.random((B, N)) + 0.05 * np.sin(np.arange(N) / 50.)[None, :]
+    det = bf.OddsRatioDetector(bf.Lightcurve(cts=cts, clc=clc[0], cle=cle[0]))
+    ctx = det.plan().ctx
+    t_api, (lnO, sk) = timeit(lambda: det.oddsratio_batch(clc, cle=cle, return_sk=True), reps=3)
+    ctx.set_timing(True)
+    det.oddsratio_batch(clc, cle=cle)
+    ctx.sync()
+    ms, nl = ctx.window_time()
+    ctx.set_timing(False)
+    units = B * (N - 54) * det.ngrid_eval
+    errs = []
+    for b in (0, 1):
+        ref, _ = orc.oddsratio(clc[b], cle[b], cts, sk=float(sk[b]))
+        errs.append(scaled_err(lnO[b], ref))
+    return {"config": "6 (extra)", "what": config6.__doc__, "B": B, "N": N, "g_eval": det.ngrid_eval, "units": units,
+            "api_batch_s": t_api, "units_per_s_api": units / t_api, "window_kernels_ms": ms, "window_kernel_launches": nl,
+            "units_per_s_window_kernels": units / (ms * 1e-3), "parity_sample": "2 curves", "parity_max_scaled_err": max(errs)}
+
+
 def main():
-    which = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5]
-    fns = {1: config1, 2: config2, 4: config4, 5: config5}
+    which = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5, 6]
+    fns = {1: config1, 2: config2, 4: config4, 5: config5, 6: config6}
     for w in which:
         if w == 3:
             print(json.dumps({"config": 3, "what": "see bench.py (the contract benchmark runs this configuration)"}))

@@ -375,11 +375,11 @@ def test_full_size_batch_properties_config3():
     assert lnO.shape == (B, N - 54) and np.all(np.isfinite(lnO))
     for b in (0, 137, 512, 1023):
         single = det.plan().detector_odds(clc[b], None, sk[b], k0=27, k1=N - 27)
-        np.testing.assert_allclose(lnO[b], single, rtol=0, atol=5e-13)
+        np.testing.assert_allclose(lnO[b], single, rtol=0, atol=2e-11)   # linear-domain table (batch) vs log-domain table (single)
     # permuting the curves of a batch permutes the output rows (no cross-talk between curves)
     perm = np.random.default_rng(0).permutation(64)
     again = det.plan().detector_odds(clc[perm], None, sk[perm], k0=27, k1=N - 27)
-    np.testing.assert_allclose(again, lnO[perm], rtol=0, atol=5e-13)
+    np.testing.assert_allclose(again, lnO[perm], rtol=0, atol=2e-11)
     for b in (3, 700):
         ref, _ = orc.oddsratio(clc[b], np.zeros(N), cts, sk=sk[b])
         assert_logodds_close(lnO[b], ref, TOL, "config3 curve %d" % b)
