@@ -786,6 +786,10 @@ struct EpiArgs {
   int hyp_nA[MAXH];
   const double* Kg; const double* lp; const double* lw; const double* inorm;
   const short* idxA; const short* idxB;
+  const int* sh_g0; const int* sh_g1;   // per shape: the run of templates that use it as their B shape
+  int hyp_B0[MAXH];
+  int hyp_nB[MAXH];
+  int S, arows;           // shapes; A-shape rows of the per-thread shared-memory slice
   int noisepoly;
   double* lnO;            // MODE 2
   double2* part;          // MODE 0: [nhyp][BK]
@@ -803,7 +807,7 @@ constexpr int EPI_TPB = 256;
 //    shared memory is better spent on occupancy.
 // Both produce (reference value, sum) pairs per hypothesis, folded into the odds the same way.
 template <int MODE, int SPT>
-__global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
+__global__ void __launch_bounds__(EPI_TPB, 3) k_epilogue(const EpiArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int G = a.G;
@@ -812,13 +816,15 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
   double* sInorm = sC + ((G + 1) & ~1);                  // [G]
   double* sCref = sInorm + ((G + 1) & ~1);               // [MAXH]
   double* sE = sCref + MAXH;                             // E(z) table
-  short* sIdx = reinterpret_cast<short*>(sE + BFL_EXPHI_SIZE);   // [G][2]
+  double* ysm = sE + BFL_EXPHI_SIZE;                     // [arows][SPT][EPI_TPB] this thread's A-shape correlations
+  int* sG01 = reinterpret_cast<int*>(ysm + (size_t)a.arows * SPT * EPI_TPB);   // [S][2]
+  short* sIdxA = reinterpret_cast<short*>(sG01 + 2 * a.S);                     // [G]
   for (int i = tid; i < G; i += EPI_TPB) {
     sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
     sInorm[i] = a.inorm[i];
-    sIdx[2 * i] = a.idxA[i];
-    sIdx[2 * i + 1] = a.idxB[i];
+    sIdxA[i] = a.idxA[i];
   }
+  for (int i = tid; i < a.S; i += EPI_TPB) { sG01[2 * i] = a.sh_g0[i]; sG01[2 * i + 1] = a.sh_g1[i]; }
   for (int i = tid; i < BFL_EXPHI_SIZE; i += EPI_TPB) sE[i] = BFL_EXPHI_TAB[i];
   __syncthreads();
   if (tid < a.nhyp) {
@@ -868,52 +874,67 @@ __global__ void __launch_bounds__(EPI_TPB) k_epilogue(const EpiArgs a) {
         if (glo >= ghi) continue;
         const bool half = a.hyp_half[h] != 0;
         {
-          // the A-shape correlations of a template are re-read through L1 (each is shared by the
-          // templates of one rise time); the B-shape value stays in registers while it is shared
-          const double* YA = a.Y + (size_t)a.hyp_A0[h] * a.BK;
-          int curB = -1;
-          double yB[SPT];
-          for (int g = glo; g < ghi; g++) {
-            const int ia = sIdx[2 * g], ib = sIdx[2 * g + 1];
-            if (ib != curB) {
-              curB = ib;
+          // The hypothesis' A-shape correlations are fetched once (coalesced, all in flight together) into
+          // this thread's shared-memory slice; B shapes are walked in order, the next one prefetched
+          // while the run of templates that share the current one is evaluated.
+          const int nA = a.hyp_nA[h], B0 = a.hyp_B0[h], nB = a.hyp_nB[h];
+          {
+            const double* YA = a.Y + (size_t)a.hyp_A0[h] * a.BK;
+            for (int ia = 0; ia < nA; ia++) {
 #pragma unroll
-              for (int j = 0; j < SPT; j++) yB[j] = __ldg(a.Y + (size_t)ib * a.BK + idx[j]);
+              for (int j = 0; j < SPT; j++) ysm[(ia * SPT + j) * EPI_TPB + tid] = __ldg(YA + (size_t)ia * a.BK + idx[j]);
             }
-            const double sc = (ia >= 0) ? sInorm[g] : 1.0;
-            double z[SPT];
+          }
+          double yB[SPT], yBn[SPT];
+          const double* YB = a.Y + (size_t)B0 * a.BK;
 #pragma unroll
-            for (int j = 0; j < SPT; j++)
-              z[j] = (ia >= 0) ? sc * (__ldg(YA + (size_t)ia * a.BK + idx[j]) + yB[j]) : yB[j];
-            if constexpr (lin) {
-              const double cg = sC[g];
+          for (int j = 0; j < SPT; j++) yBn[j] = __ldg(YB + idx[j]);
+          for (int ib = 0; ib < nB; ib++) {
+            const double* YBn = YB + (size_t)min(ib + 1, nB - 1) * a.BK;
 #pragma unroll
-              for (int j = 0; j < SPT; j++) {
-                big = big || (fabs(z[j]) > ZC);
-                const double e = half ? exphi_eval(z[j], sE) : exp_nonpos_poly(fma(0.5 * z[j], z[j], -0.5 * ZC * ZC));
-                sm[j] = fma(cg, e, sm[j]);
-              }
-            } else {
-              const double kg = sK[g];
-              double val[SPT];
-              if (half) {
-                bool far_ = false;
+            for (int j = 0; j < SPT; j++) { yB[j] = yBn[j]; yBn[j] = __ldg(YBn + idx[j]); }
+            const int g0 = sG01[2 * (B0 + ib)], g1 = sG01[2 * (B0 + ib) + 1];
+            for (int g = g0; g < g1; g++) {
+              double z[SPT];
+              if (nA > 0) {
+                const double sc = sInorm[g];
+                const double* ya = ysm + (size_t)sIdxA[g] * SPT * EPI_TPB + tid;
 #pragma unroll
-                for (int j = 0; j < SPT; j++) {
-                  val[j] = kg + phi_tab_rows(z[j], BFL_PHI_TAB);
-                  far_ = far_ || (z[j] < BFL_PHI_ZFAR);
-                }
-                if (far_) {
-#pragma unroll
-                  for (int j = 0; j < SPT; j++)
-                    if (z[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(z[j]);
-                }
+                for (int j = 0; j < SPT; j++) z[j] = sc * (ya[j * EPI_TPB] + yB[j]);
               } else {
 #pragma unroll
-                for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
+                for (int j = 0; j < SPT; j++) z[j] = yB[j];
               }
+              if constexpr (lin) {
+                const double cg = sC[g];
 #pragma unroll
-              for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
+                for (int j = 0; j < SPT; j++) {
+                  big = big || (fabs(z[j]) > ZC);
+                  const double e = half ? exphi_eval(z[j], sE) : exp_nonpos_poly(fma(0.5 * z[j], z[j], -0.5 * ZC * ZC));
+                  sm[j] = fma(cg, e, sm[j]);
+                }
+              } else {
+                const double kg = sK[g];
+                double val[SPT];
+                if (half) {
+                  bool far_ = false;
+#pragma unroll
+                  for (int j = 0; j < SPT; j++) {
+                    val[j] = kg + phi_tab_rows(z[j], BFL_PHI_TAB);
+                    far_ = far_ || (z[j] < BFL_PHI_ZFAR);
+                  }
+                  if (far_) {
+#pragma unroll
+                    for (int j = 0; j < SPT; j++)
+                      if (z[j] < BFL_PHI_ZFAR) val[j] = kg + phi_half_far(z[j]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < SPT; j++) val[j] = fma(0.5 * z[j], z[j], kg);
+                }
+#pragma unroll
+                for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
+              }
             }
           }
         }
@@ -960,15 +981,22 @@ static size_t corr_smem_bytes(int S, int KT) {
   const int wstride = (32 * KT + 2 * 27 + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)S * 56);
 }
-static size_t epi_smem_bytes(int G, int SPT) {
-  (void)SPT;
-  return sizeof(double) * (size_t)(3 * ((G + 1) & ~1) + MAXH + BFL_EXPHI_SIZE) + sizeof(short) * (size_t)(2 * G + 8);
+static size_t epi_smem_bytes(int G, int S, int arows, int SPT) {
+  return sizeof(double) * ((size_t)(3 * ((G + 1) & ~1) + MAXH + BFL_EXPHI_SIZE) + (size_t)arows * SPT * EPI_TPB) +
+         sizeof(int) * (size_t)(2 * S) + sizeof(short) * (size_t)(G + 8);
+}
+
+static int epi_arows(const PlanView& pv) {
+  int m = 0;
+  for (int h = 0; h < pv.nhyp; h++) m = std::max(m, pv.hyp_nA[h]);
+  return m;
 }
 
 bool fast_split_fits(const PlanView& pv) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_SPLIT"); off = (e && atoi(e)) ? 1 : 0; }
-  return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && epi_smem_bytes(pv.G, 2) <= 200 * 1024;
+  return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && pv.wsep_ok &&
+         epi_smem_bytes(pv.G, pv.S, epi_arows(pv), 2) <= 100 * 1024;   // wsep_ok: templates grouped by B shape
 }
 
 // mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
@@ -1008,10 +1036,12 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   a.B = sv.B; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
+  for (int h = 0; h < pv.nhyp; h++) { a.hyp_B0[h] = pv.hyp_B0[h]; a.hyp_nB[h] = pv.hyp_nB[h]; }
   a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = epi_arows(pv);
   a.noisepoly = noisepoly; a.lnO = d_lnO; a.part = sc.part;
   constexpr int SPT = 2;
-  const size_t smem2 = epi_smem_bytes(pv.G, SPT);
+  const size_t smem2 = epi_smem_bytes(pv.G, pv.S, a.arows, SPT);
   const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
 #define BFL_EPI(MODE_)                                                                                      \
   do {                                                                                                      \
