@@ -796,6 +796,16 @@ struct EpiArgs {
 };
 
 constexpr int EPI_TPB = 256;
+#ifndef BFL_EPI_SPT
+#define BFL_EPI_SPT 2      // samples per thread of the epilogue kernel
+#endif
+#ifndef BFL_EPI_MINB
+#define BFL_EPI_MINB 3
+#endif
+#ifndef BFL_EPI_GU
+#define BFL_EPI_GU 1
+#endif
+constexpr int EPI_GU = BFL_EPI_GU;     // templates evaluated together by the linear-domain loop (2 measured no faster)
 
 // Two evaluation strategies per thread tile:
 //  * LINEAR (first): nearly every sample is noise, where every |z_g| is a few units.  Then the grid sum
@@ -807,7 +817,7 @@ constexpr int EPI_TPB = 256;
 //    shared memory is better spent on occupancy.
 // Both produce (reference value, sum) pairs per hypothesis, folded into the odds the same way.
 template <int MODE, int SPT>
-__global__ void __launch_bounds__(EPI_TPB, 3) k_epilogue(const EpiArgs a) {
+__global__ void __launch_bounds__(EPI_TPB, BFL_EPI_MINB) k_epilogue(const EpiArgs a) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
   const int G = a.G;
@@ -894,6 +904,36 @@ __global__ void __launch_bounds__(EPI_TPB, 3) k_epilogue(const EpiArgs a) {
 #pragma unroll
             for (int j = 0; j < SPT; j++) { yB[j] = yBn[j]; yBn[j] = __ldg(YBn + idx[j]); }
             const int g0 = sG01[2 * (B0 + ib)], g1 = sG01[2 * (B0 + ib) + 1];
+            if constexpr (lin) {
+              // EPI_GU templates per iteration: EPI_GU * SPT independent dependency chains per thread
+              for (int g = g0; g < g1; g += EPI_GU) {
+                double z[EPI_GU][SPT], cg[EPI_GU];
+#pragma unroll
+                for (int u = 0; u < EPI_GU; u++) {
+                  const int gu = min(g + u, g1 - 1);
+                  cg[u] = (g + u < g1) ? sC[gu] : 0.0;
+                  if (nA > 0) {
+                    const double sc = sInorm[gu];
+                    const double* ya = ysm + (size_t)sIdxA[gu] * SPT * EPI_TPB + tid;
+#pragma unroll
+                    for (int j = 0; j < SPT; j++) z[u][j] = sc * (ya[j * EPI_TPB] + yB[j]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < SPT; j++) z[u][j] = yB[j];
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < EPI_GU; u++) {
+#pragma unroll
+                  for (int j = 0; j < SPT; j++) {
+                    big = big || ((__double2hiint(z[u][j]) & 0x7fffffff) >= 0x40180000);   // |z| >= 6 (or NaN)
+                    const double e = half ? exphi_eval(z[u][j], sE)
+                                          : exp_nonpos_poly(fma(0.5 * z[u][j], z[u][j], -0.5 * ZC * ZC));
+                    sm[j] = fma(cg[u], e, sm[j]);
+                  }
+                }
+              }
+            } else {
             for (int g = g0; g < g1; g++) {
               double z[SPT];
               if (nA > 0) {
@@ -905,15 +945,7 @@ __global__ void __launch_bounds__(EPI_TPB, 3) k_epilogue(const EpiArgs a) {
 #pragma unroll
                 for (int j = 0; j < SPT; j++) z[j] = yB[j];
               }
-              if constexpr (lin) {
-                const double cg = sC[g];
-#pragma unroll
-                for (int j = 0; j < SPT; j++) {
-                  big = big || (fabs(z[j]) > ZC);
-                  const double e = half ? exphi_eval(z[j], sE) : exp_nonpos_poly(fma(0.5 * z[j], z[j], -0.5 * ZC * ZC));
-                  sm[j] = fma(cg, e, sm[j]);
-                }
-              } else {
+              if constexpr (!lin) {
                 const double kg = sK[g];
                 double val[SPT];
                 if (half) {
@@ -936,6 +968,7 @@ __global__ void __launch_bounds__(EPI_TPB, 3) k_epilogue(const EpiArgs a) {
                 for (int j = 0; j < SPT; j++) lse_push_poly(mx[j], sm[j], val[j]);
               }
             }
+            }   // log-domain loop
           }
         }
         // hypothesis finished: partial out (MODE 0) or fold into numerator / denominator (MODE 2)
@@ -996,7 +1029,7 @@ bool fast_split_fits(const PlanView& pv) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_SPLIT"); off = (e && atoi(e)) ? 1 : 0; }
   return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && pv.wsep_ok &&
-         epi_smem_bytes(pv.G, pv.S, epi_arows(pv), 2) <= 100 * 1024;   // wsep_ok: templates grouped by B shape
+         epi_smem_bytes(pv.G, pv.S, epi_arows(pv), BFL_EPI_SPT) <= 50 * 1024 * BFL_EPI_SPT;   // wsep_ok: templates grouped by B shape
 }
 
 // mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
@@ -1040,7 +1073,7 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
   a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = epi_arows(pv);
   a.noisepoly = noisepoly; a.lnO = d_lnO; a.part = sc.part;
-  constexpr int SPT = 2;
+  constexpr int SPT = BFL_EPI_SPT;
   const size_t smem2 = epi_smem_bytes(pv.G, pv.S, a.arows, SPT);
   const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
 #define BFL_EPI(MODE_)                                                                                      \

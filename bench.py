@@ -314,10 +314,10 @@ def run_ours(args, rank, local_rank, world):
     flops_strict = float(B) * interior * N_TEMPLATES * 2.0 * det.bglen
     # what the kernels really execute: the flare grid is held in separable form (rise x decay shapes), so
     # only `shapes` correlations of 2W flop are done per sample (k_corr_shapes), plus per template ~2 flop
-    # to assemble z and ~52 flop of epilogue (degree-4 phi polynomial, degree-11 exp, log-sum-exp update;
-    # k_epilogue)
+    # to assemble z and ~34 flop of epilogue (E(z) = exp(phi(z)) from one 16-byte table row: node
+    # derivatives, cubic in z - z_k, degree-5 series, one FMA into the linear-domain grid sum; k_epilogue)
     shapes = plan.shape_count if plan.shape_count > 0 else N_TEMPLATES
-    flops_exec = float(B) * interior * (shapes * 2.0 * det.bglen + N_TEMPLATES * 54.0)
+    flops_exec = float(B) * interior * (shapes * 2.0 * det.bglen + N_TEMPLATES * 36.0)
     win_avg_ms = win_ms / max(win_n, 1)
     achieved = flops_launch / (win_avg_ms * 1e-3) / 1e12
     peaks = {}

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -4
-ncu --set full --clock-control none --import-source on -k regex:k_epilogue -c 1 -s 3 -o gpurun_out/epi_r1b -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_epi.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_epilogue -c 1 -s 3 -o gpurun_out/epi_r1c -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_epi.log 2>&1
 tail -2 gpurun_out/ncu_epi.log
