@@ -69,6 +69,8 @@ SIGNATURES = {
     "bfl_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "bfl_ctx_window_time": (C.c_int, [C.c_void_p, _dp, _i64p]),
     "bfl_count_regions_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
+    "bfl_count_regions_total_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
+                                              C.c_void_p]),
     "bfl_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(Hypothesis), C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "bfl_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -150,8 +152,14 @@ class Context:
         check(self.lib.bfl_ctx_window_time(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def count_regions_dev(self, d_lnO, B, n, thresh, d_counts):
-        check(self.lib.bfl_count_regions_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_counts))
+    def count_regions_dev(self, d_lnO, B, n, thresh, d_counts, d_totals=None):
+        """Per-curve region counts (device addresses); with ``d_totals`` also accumulates the batch totals
+        [regions, curves with a region] into that 2-element int64 device array."""
+        if d_totals is None:
+            check(self.lib.bfl_count_regions_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_counts))
+        else:
+            check(self.lib.bfl_count_regions_total_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_counts,
+                                                       d_totals))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -814,7 +814,17 @@ int bfl_count_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n,
   if (!c || !d_lnO || !d_counts || B < 1 || n < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_count_regions_dev");
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)B, c->stream));
-  CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, c->stream, &c->stats));
+  CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, nullptr, c->stream, &c->stats));
+  return BFL_OK;
+}
+
+int bfl_count_regions_total_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n, double thresh, int64_t* d_counts,
+                                int64_t* d_totals) {
+  if (!c || !d_lnO || !d_counts || !d_totals || B < 1 || n < 1)
+    return fail(BFL_ERR_ARG, "bad argument to bfl_count_regions_total_dev");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)B, c->stream));
+  CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, d_totals, c->stream, &c->stats));
   return BFL_OK;
 }
 

@@ -2606,19 +2606,24 @@ cudaError_t launch_threshold_edges(const double* d_lnO, int64_t n, double thresh
 
 // number of region starts per curve (a start = above threshold and predecessor not above)
 __global__ void k_count_regions(const double* __restrict__ lnO, int B, int64_t n, double thresh,
-                                unsigned long long* counts) {
+                                unsigned long long* counts, unsigned long long* totals) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * B) return;
   const int64_t k = i % n;
   if (!(lnO[i] > thresh)) return;
   if (k > 0 && lnO[i - 1] > thresh) return;
-  atomicAdd(&counts[i / n], 1ULL);
+  const unsigned long long before = atomicAdd(&counts[i / n], 1ULL);
+  if (totals) {                                   // [0] regions in the batch, [1] curves with at least one
+    atomicAdd(&totals[0], 1ULL);
+    if (before == 0ULL) atomicAdd(&totals[1], 1ULL);
+  }
 }
 
 cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
-                                 cudaStream_t s, LaunchStats* st) {
+                                 int64_t* d_totals, cudaStream_t s, LaunchStats* st) {
   const int64_t tot = n * B;
-  k_count_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts);
+  k_count_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts,
+                                                                (unsigned long long*)d_totals);
   st->launches++;
   return cudaGetLastError();
 }

@@ -139,7 +139,7 @@ cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int ns
                               int64_t* d_maxidx, cudaStream_t s, LaunchStats* st);
 
 cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
-                                 cudaStream_t s, LaunchStats* st);
+                                 int64_t* d_totals, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
                             cudaStream_t s, LaunchStats* st);
 cudaError_t launch_ps_sigma(const double2* d_X, int64_t N, int B, double estfrac, double* d_sk, cudaStream_t s,

@@ -216,23 +216,21 @@ def run_ours(args, rank, local_rank, world):
     d_out = torch.empty((B, NK), dtype=torch.float64, device=dev)
     d_cnt = torch.zeros(B, dtype=torch.int64, device=dev)
     d_tot = torch.zeros((args.steps + args.warmup + 1, 2), dtype=torch.int64, device=dev)
-    pending = []
+    d_red = torch.zeros_like(d_tot)              # all ranks' totals
     torch.cuda.synchronize()
 
     def step(i):
         j = i % NB
         plan.detector_odds_dev(d_in[j].data_ptr(), 0, True, d_sk[j].data_ptr(), B, N, 0, N, K0, K1, d_out.data_ptr())
-        ctx.count_regions_dev(d_out.data_ptr(), B, NK, THRESH, d_cnt.data_ptr())
-        if world > 1:
-            # NCCL over NVLink: detection counts only (regions, curves with a detection); the
-            # collective is asynchronous and overlaps the next batch, all handles are waited on
-            # before the timed region ends
-            torch.stack(((d_cnt).sum(), (d_cnt > 0).sum()), out=d_tot[i])
-            pending.append(dist.all_reduce(d_tot[i], async_op=True))
+        # per-curve region counts + this batch's totals (regions, curves with a detection) in row i
+        ctx.count_regions_dev(d_out.data_ptr(), B, NK, THRESH, d_cnt.data_ptr(), d_tot[i].data_ptr())
 
     def drain():
-        while pending:
-            pending.pop().wait()
+        # NCCL over NVLink: detection counters only -- one all-reduce of the per-batch totals for the
+        # whole job, issued on the kernels' stream inside the timed region
+        d_red.copy_(d_tot)
+        if world > 1:
+            dist.all_reduce(d_red)
 
     peak_tf, _ = _lib.fp64_peak(ctx, 4096)        # roofline denominator, measured live (burst)
 
@@ -302,6 +300,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- sanity: the last e2e output against what the device path produced for that batch --
     lnO_host = out_host.numpy()
     n_det = int((d_cnt > 0).sum().item())
+    job = d_red[args.warmup:args.warmup + args.steps].sum(dim=0).tolist()   # all ranks, timed steps
 
     if rank != 0:
         if world > 1:
@@ -366,7 +365,8 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "detections": {"curves_with_detection": n_det, "curves": B}}
+            "detections": {"curves_with_detection": n_det, "curves": B,
+                           "job_regions_all_ranks": int(job[0]), "job_curves_with_detection_all_ranks": int(job[1])}}
 
     if not args.no_cpu_baseline and world == 1:
         nc = min(args.cpu_curves, B)

@@ -159,6 +159,12 @@ int bfl_detector_odds_dev(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const dou
 int bfl_count_regions_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh,
                           int64_t* d_counts);
 
+/* Same, and in addition ACCUMULATES into d_totals[2] (device, int64; not cleared by the call): [0] the number
+ * of regions in the batch, [1] the number of curves with at least one region -- the two counters a
+ * multi-GPU search reduces over ranks (one small NCCL all-reduce per job instead of per batch). */
+int bfl_count_regions_total_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh,
+                                int64_t* d_counts, int64_t* d_totals);
+
 /* ---- OddsRatioDetector.thresholder (find.py:915-1019) on device ----------------------
  * contiguous regions of lnO > thresh, expanded by `expand` and merged; per region the
  * maximum and its index.  lnO host [n]; segs host [max_segs][2] (start, stop), maxval /

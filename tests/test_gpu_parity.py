@@ -553,3 +553,23 @@ def test_kepler_search_from_fits_files_vs_reference(tmp_path):
     # restart: already analysed stars are skipped
     again = bf.flare_search(paths, threshold=16.5, outdict=out)
     assert again["No. stars analysed"] == 3
+
+
+@pytest.mark.gpu
+def test_count_regions_with_batch_totals():
+    import torch
+    rng = np.random.default_rng(3)
+    B, n = 7, 500
+    lnO = rng.standard_normal((B, n)) * 3
+    lnO[2] = -5.0                                    # a curve without detections
+    ctx = _lib.default_context()
+    d = torch.from_numpy(lnO).cuda()
+    d_cnt = torch.empty(B, dtype=torch.int64, device="cuda")
+    d_tot = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):                               # totals accumulate over calls
+        ctx.count_regions_dev(d.data_ptr(), B, n, 2.0, d_cnt.data_ptr(), d_tot.data_ptr())
+    ctx.sync()
+    want = np.array([len(orc.contiguous_regions(row > 2.0)) for row in lnO])
+    np.testing.assert_array_equal(d_cnt.cpu().numpy(), want)
+    assert d_tot.cpu().tolist() == [2 * int(want.sum()), 2 * int((want > 0).sum())]
