@@ -265,6 +265,9 @@ class Plan:
         if cle is not None and cle.shape != clc.shape:
             raise ValueError("batch shapes of clc and cle do not agree")
         k1 = N if k1 is None else int(k1)
+        k0 = int(k0)
+        if not 0 <= k0 < k1 <= N:
+            raise ValueError("bad sample range [%d, %d) for a series of %d samples" % (k0, k1, N))
         lnO = np.empty((B, k1 - k0))
         marg = np.empty((self.nhyp + 1, B, k1 - k0)) if want_marg else None
         sk_out = np.empty(B) if want_sk else None

@@ -228,7 +228,7 @@ class OddsRatioDetector:
             # sum-of-log-sigma constant of general.pyx:216-221
             noisevar = sk ** 2 + cle ** 2
             lnO = lnO + float(np.sum(np.log(np.sqrt(noisevar))))
-        return list(lnO), np.copy(lc.cts[h:N - h])
+        return np.asarray(lnO).ravel().tolist(), np.copy(lc.cts[h:N - h])
 
     def noise_spec(self, detrended=False):
         """Device-side description of this detector's noise estimate (``bfl_noise_spec``)."""

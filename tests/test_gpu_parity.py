@@ -573,3 +573,74 @@ def test_count_regions_with_batch_totals():
     want = np.array([len(orc.contiguous_regions(row > 2.0)) for row in lnO])
     np.testing.assert_array_equal(d_cnt.cpu().numpy(), want)
     assert d_tot.cpu().tolist() == [2 * int(want.sum()), 2 * int((want > 0).sum())]
+
+
+# ---- edge cases: minimum / ragged sizes, widest window, fully masked grids, bad arguments
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [55, 56, 60, 109, 110])
+def test_shortest_series_vs_oracle(N, monkeypatch):
+    """N == bglen (every window truncated) up to N == 2*bglen (first full windows): the reference's
+    edge handling bayes.py:320-327 with as few as 28 samples in a window"""
+    rng = np.random.default_rng(N)
+    ts = np.arange(N) * DT
+    clc = rng.standard_normal(N) + orc.flare_model(ts, ts[N // 2], 6., 1000., 3000.)
+    _force_sk(monkeypatch, 1.07)
+    pr = {"t0": (np.inf,), "amp": (1.,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3)}
+    B = bf.Bayes(_lc(ts, clc), bf.Flare(ts, amp=1, paramranges=pr))
+    B.bayes_factors_marg_poly_bgd()
+    ref, _, refbg = orc.bayes_factors(clc, np.zeros(N), ts, "flare", pr, 1.07, with_background=True)
+    assert B.lnBmargAmp.shape == (1, 3, 3, 1, N)
+    assert_logodds_close(B.lnBmargAmp, ref, TOL, "N=%d" % N)
+    det = bf.OddsRatioDetector(_lc(ts, clc), ignoreedges=False)
+    monkeypatch.setattr(det, "noise_sigma", lambda lightcurve=None: 1.07)
+    lnO, tso = det.oddsratio()
+    refO, _ = orc.oddsratio(clc, np.zeros(N), ts, ignoreedges=False, sk=1.07)
+    assert len(lnO) == N
+    assert_logodds_close(lnO, refO, TOL, "detector N=%d" % N)
+
+
+@pytest.mark.gpu
+def test_too_short_series_and_bad_arguments():
+    ts = np.arange(54) * DT
+    det = bf.OddsRatioDetector(_lc(np.arange(300) * DT, np.zeros(300)))
+    plan = det.plan()
+    with pytest.raises(_lib.BflError):                      # bayes.py: bglen greater than the data length
+        plan.detector_odds(np.zeros(54), None, 1.0)
+    with pytest.raises(ValueError):                         # bad sample range
+        plan.detector_odds(np.zeros(300), None, 1.0, k0=200, k1=100)
+    with pytest.raises(ValueError):                         # ragged batch: sigma count differs from curve count
+        plan.detector_odds(np.zeros((3, 300)), None, np.ones(2))
+    with pytest.raises(ValueError):
+        plan.detector_odds(np.zeros((3, 300)), np.zeros((2, 300)), np.ones(3))
+    with pytest.raises(ValueError):                         # neither sigma nor a noise specification
+        plan.detector_odds(np.zeros(300), None, None)
+    # a sub-range of samples equals the same slice of the full run
+    rng = np.random.default_rng(1)
+    clc = rng.standard_normal(300)
+    full = plan.detector_odds(clc, None, 1.0)
+    part = plan.detector_odds(clc, None, 1.0, k0=13, k1=200)
+    np.testing.assert_allclose(part, full[13:200], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_widest_window_and_fully_masked_grid(monkeypatch):
+    """bglen = 255 (the ABI's limit) against the oracle; a flare grid whose every point has tau_gauss >
+    tau_exp (prior -inf everywhere) marginalises to -inf, like the reference's masked rows"""
+    rng = np.random.default_rng(255)
+    N = 700
+    ts = np.arange(N) * 60.0
+    clc = rng.standard_normal(N) + orc.flare_model(ts, ts[350], 5., 600., 2400.)
+    _force_sk(monkeypatch, 0.98)
+    pr = {"t0": (np.inf,), "amp": (1.,), "taugauss": (0, 1800, 2), "tauexp": (600, 3600, 3)}
+    B = bf.Bayes(_lc(ts, clc), bf.Flare(ts, amp=1, paramranges=pr))
+    B.bayes_factors_marg_poly_bgd(bglen=255, bgorder=3)
+    ref, _ = orc.bayes_factors(clc, np.zeros(N), ts, "flare", pr, 0.98, bglen=255, bgorder=3)
+    assert_logodds_close(B.lnBmargAmp, ref, TOL, "bglen 255")
+    with pytest.raises(_lib.BflError):
+        _lib.Plan(_lib.default_context(), 257, bbayes.background_models(257, 3), np.arange(257) * 60., [])
+    prm = {"t0": (np.inf,), "amp": (1.,), "taugauss": (7200, 9000, 2), "tauexp": (600, 3600, 2)}
+    Bm = bf.Bayes(_lc(ts, clc), bf.Flare(ts, amp=1, paramranges=prm))
+    Bm.bayes_factors_marg_poly_bgd()
+    assert np.all(Bm.lnBmargAmp == -np.inf)
+    refm, rr = orc.bayes_factors(clc, np.zeros(N), ts, "flare", prm, 0.98)
+    assert np.all(refm == -np.inf)
