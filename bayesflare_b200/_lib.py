@@ -71,6 +71,10 @@ SIGNATURES = {
     "bfl_count_regions_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p]),
     "bfl_count_regions_total_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p,
                                               C.c_void_p]),
+    "bfl_sweep_simulate_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bfl_sweep_score_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_double,
+                                      C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bfl_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(Hypothesis), C.c_int,
                                   C.POINTER(C.c_void_p)]),
     "bfl_plan_destroy": (C.c_int, [C.c_void_p]),
@@ -135,6 +139,7 @@ class Context:
         h = C.c_void_p()
         check(self.lib.bfl_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
+        self.device = int(device)          # -1: the device that was current at creation
 
     def sync(self):
         check(self.lib.bfl_ctx_sync(self.handle))
@@ -151,6 +156,21 @@ class Context:
         ms, n = C.c_double(0), C.c_int64(0)
         check(self.lib.bfl_ctx_window_time(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def sweep_simulate_dev(self, seed, first, B, N, halfwin, dt, nstd, sinusoid_amp, snr_lo, snr_hi, inject, d_clc, d_truth):
+        """Simulate a batch of light curves on the device (device addresses; see ``bfl_sweep_simulate_dev``)."""
+        check(self.lib.bfl_sweep_simulate_dev(self.handle, int(seed), int(first), int(B), int(N), int(halfwin), float(dt),
+                                              float(nstd), float(sinusoid_amp), float(snr_lo), float(snr_hi),
+                                              1 if inject else 0, d_clc, d_truth))
+
+    def sweep_score_dev(self, d_lnO, B, nk, halfwin, d_truth, thresh, nbins, snr_max, d_injected, d_detected, d_counters):
+        """Match detections to injections and accumulate the efficiency histograms (``bfl_sweep_score_dev``)."""
+        check(self.lib.bfl_sweep_score_dev(self.handle, d_lnO, int(B), int(nk), int(halfwin), d_truth, float(thresh),
+                                           int(nbins), float(snr_max), d_injected, d_detected, d_counters))
+
+    def noise_sigma_dev(self, spec, d_clc, B, N, d_sk):
+        """Device-resident noise estimate (``bfl_noise_sigma_dev``)."""
+        check(self.lib.bfl_noise_sigma_dev(self.handle, C.byref(spec[0]), d_clc, int(B), int(N), d_sk))
 
     def count_regions_dev(self, d_lnO, B, n, thresh, d_counts, d_totals=None):
         """Per-curve region counts (device addresses); with ``d_totals`` also accumulates the batch totals

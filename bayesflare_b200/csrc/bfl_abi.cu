@@ -818,6 +818,31 @@ int bfl_count_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n,
   return BFL_OK;
 }
 
+int bfl_sweep_simulate_dev(bfl_ctx* c, uint64_t seed, int64_t first, int32_t B, int32_t N, int32_t halfwin, double dt,
+                           double nstd, double sinusoid_amp, double snr_lo, double snr_hi, int32_t inject, double* d_clc,
+                           double* d_truth) {
+  if (!c || !d_clc || !d_truth) return fail(BFL_ERR_ARG, "null argument to bfl_sweep_simulate_dev");
+  if (B < 1 || N < 8 || N > 8192) return fail(BFL_ERR_UNSUPPORTED, "bfl_sweep_simulate_dev supports 8 <= N <= 8192 samples");
+  if (halfwin < 0 || 2 * halfwin + 2 > N || !(dt > 0.0) || !(nstd > 0.0) || snr_hi < snr_lo)
+    return fail(BFL_ERR_ARG, "bad argument to bfl_sweep_simulate_dev");
+  CK(cudaSetDevice(c->device));
+  CK(launch_sweep_simulate(seed, first, B, N, halfwin, dt, nstd, sinusoid_amp, snr_lo, snr_hi, inject, d_clc, d_truth,
+                           c->stream, &c->stats));
+  return BFL_OK;
+}
+
+int bfl_sweep_score_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t nk, int32_t halfwin, const double* d_truth,
+                        double thresh, int32_t nbins, double snr_max, int64_t* d_injected, int64_t* d_detected,
+                        int64_t* d_counters) {
+  if (!c || !d_lnO || !d_truth || !d_injected || !d_detected || !d_counters || B < 1 || nk < 1 || nbins < 1 ||
+      !(snr_max > 0.0))
+    return fail(BFL_ERR_ARG, "bad argument to bfl_sweep_score_dev");
+  CK(cudaSetDevice(c->device));
+  CK(launch_sweep_score(d_lnO, B, nk, halfwin, d_truth, thresh, nbins, snr_max, d_injected, d_detected, d_counters,
+                        c->stream, &c->stats));
+  return BFL_OK;
+}
+
 int bfl_count_regions_total_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n, double thresh, int64_t* d_counts,
                                 int64_t* d_totals) {
   if (!c || !d_lnO || !d_counts || !d_totals || B < 1 || n < 1)

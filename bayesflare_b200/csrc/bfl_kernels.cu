@@ -2854,3 +2854,199 @@ cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_
 }
 
 }  // namespace bfl
+
+// ======================================================================================
+// Injection sweep on the device (scripts/flare_detection_efficiency.py:399-651)
+// ======================================================================================
+namespace bfl {
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based, so realisation r gets the same stream whatever
+// the batch or rank that simulates it.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ double u53(unsigned a, unsigned b) {     // uniform in [0, 1)
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+struct SimArgs {
+  unsigned long long seed;
+  long long first;          // index of the batch's first realisation
+  int B, N, H;
+  double dt, nstd, sinusoid_amp, snr_lo, snr_hi;
+  int inject;
+  double* clc;              // [B][N]
+  double* truth;            // [B][4]  idx, snr, taugauss, tauexp
+};
+
+// One CTA per light curve: white noise (Box-Muller on Philox), optional low-frequency sinusoid, one
+// injected flare with tau_gauss <= tau_exp scaled to a uniform signal-to-noise ratio
+// (flare_detection_efficiency.py:262-289, 321-335, 416-434, 483-487), median removed as
+// Lightcurve.dcoffset does (data.py:271-277; block-wide bitonic sort).
+__global__ void __launch_bounds__(256) k_sweep_simulate(const SimArgs a) {
+  extern __shared__ double smem[];
+  const int N = a.N, tid = threadIdx.x, T = blockDim.x;
+  int NP = 1;
+  while (NP < N) NP <<= 1;
+  double* x = smem;           // [N]
+  double* srt = smem + N;     // [NP]
+  __shared__ double red[256];
+  __shared__ double par[8];
+  const long long real = a.first + blockIdx.x;
+  const uint2 key = make_uint2((unsigned)a.seed, (unsigned)(a.seed >> 32));
+  const unsigned r_lo = (unsigned)real, r_hi = (unsigned)((unsigned long long)real >> 32);
+
+  for (int p = tid; 2 * p < N; p += T) {
+    const uint4 v = philox4x32(make_uint4((unsigned)p, r_lo, r_hi, 0u), key);
+    const double u1 = u53(v.x, v.y) + 5.5511151231257827e-17, u2 = u53(v.z, v.w);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    x[2 * p] = a.nstd * r * c;
+    if (2 * p + 1 < N) x[2 * p + 1] = a.nstd * r * s;
+  }
+  if (tid == 0) {
+    // per-realisation parameters from a separate counter plane (w = 1)
+    unsigned q = 0;
+    auto next = [&](double& u_a, double& u_b) {
+      const uint4 v = philox4x32(make_uint4(q++, r_lo, r_hi, 1u), key);
+      u_a = u53(v.x, v.y); u_b = u53(v.z, v.w);
+    };
+    double ua, ub;
+    next(ua, ub);
+    const double amp = ua * a.sinusoid_amp * a.nstd;
+    const double f = 1.0 / (31.0 * 86400.0) + ub * (1.0 / (2.0 * 86400.0) - 1.0 / (31.0 * 86400.0));
+    next(ua, ub);
+    const double phase = 2.0 * ua;                         // in units of pi
+    int idx = a.H + (int)(ub * (double)(N - 2 * a.H - 1));  // randint(h, N-h-1)
+    idx = min(idx, N - a.H - 2);
+    next(ua, ub);
+    const double te = 1800.0 + ua * 9000.0;
+    double tg = ub * 5400.0;
+    while (tg > te) { next(ua, ub); tg = ua * 5400.0; }   // redrawn until tau_gauss <= tau_exp
+    next(ua, ub);
+    const double snr = a.snr_lo + ua * (a.snr_hi - a.snr_lo);
+    par[0] = amp; par[1] = f; par[2] = phase; par[3] = (double)idx; par[4] = te; par[5] = tg; par[6] = snr;
+  }
+  __syncthreads();
+  const double amp = par[0], f = par[1], phase = par[2], te = par[4], tg = par[5], snr = par[6];
+  const int idx = (int)par[3];
+  if (a.sinusoid_amp > 0.0)
+    for (int i = tid; i < N; i += T) x[i] += amp * sinpi(2.0 * f * ((double)i * a.dt) + phase);
+  if (a.inject) {
+    const int lo = max(0, idx - 4 * a.H), hi = min(N, idx + 12 * a.H);   // the template is negligible outside
+    auto flare = [&](int i) {                                           // Flare.model, models/model.py:197-252
+      const double t = (double)(i - idx) * a.dt;
+      if (i == idx) return 1.0;
+      if (i < idx) return tg > 0.0 ? exp(-t * t / (2.0 * tg * tg)) : 0.0;
+      return te > 0.0 ? exp(-t / te) : 0.0;
+    };
+    double s2 = 0.0;
+    for (int i = lo + tid; i < hi; i += T) { const double m = flare(i); s2 = fma(m, m, s2); }
+    red[tid] = s2;
+    __syncthreads();
+    for (int o = T / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    const double scale = snr * a.nstd / sqrt(red[0]);
+    for (int i = lo + tid; i < hi; i += T) x[i] += flare(i) * scale;
+  }
+  __syncthreads();
+  // median: bitonic sort of a padded copy
+  for (int i = tid; i < NP; i += T) srt[i] = i < N ? x[i] : __longlong_as_double(0x7ff0000000000000LL);
+  __syncthreads();
+  for (int k = 2; k <= NP; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NP; i += T) {
+        const int l = i ^ j;
+        if (l > i) {
+          const double vi = srt[i], vl = srt[l];
+          const bool up = (i & k) == 0;
+          if ((vi > vl) == up) { srt[i] = vl; srt[l] = vi; }
+        }
+      }
+      __syncthreads();
+    }
+  const double med = (N & 1) ? srt[N / 2] : 0.5 * (srt[N / 2 - 1] + srt[N / 2]);
+  double* out = a.clc + (size_t)blockIdx.x * N;
+  for (int i = tid; i < N; i += T) out[i] = x[i] - med;
+  if (tid == 0) {
+    double* t = a.truth + (size_t)blockIdx.x * 4;
+    t[0] = a.inject ? (double)idx : -1.0; t[1] = snr; t[2] = tg; t[3] = te;
+  }
+}
+
+cudaError_t launch_sweep_simulate(unsigned long long seed, long long first, int B, int N, int H, double dt, double nstd,
+                                  double sinusoid_amp, double snr_lo, double snr_hi, int inject, double* d_clc,
+                                  double* d_truth, cudaStream_t s, LaunchStats* st) {
+  SimArgs a{seed, first, B, N, H, dt, nstd, sinusoid_amp, snr_lo, snr_hi, inject, d_clc, d_truth};
+  int NP = 1;
+  while (NP < N) NP <<= 1;
+  const size_t smem = sizeof(double) * (size_t)(N + NP);
+  cudaError_t e = cudaFuncSetAttribute(k_sweep_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_sweep_simulate<<<B, 256, smem, s>>>(a);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+// One thread per curve: above-threshold runs expanded by +-2 samples and merged when they touch
+// (flare_detection_efficiency.py:521-580); the region holding the injection index is a detection, every
+// other region a false positive (:586-612).  Histograms over signal-to-noise ratio as np.histogram.
+__global__ void k_sweep_score(const double* __restrict__ lnO, int B, int64_t nk, int h, const double* __restrict__ truth,
+                              double thresh, int nbins, double snr_max, unsigned long long* injected,
+                              unsigned long long* detected, unsigned long long* counters) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* row = lnO + (size_t)b * nk;
+  const int64_t inj = (int64_t)truth[4 * b] - h;           // injection index in the edge-trimmed series
+  const bool has_inj = truth[4 * b] >= 0.0;
+  int64_t rs = -1, re = -1;
+  int nfalse = 0, nreg = 0;
+  bool hit = false;
+  auto close_region = [&]() {
+    if (rs < 0) return;
+    nreg++;
+    if (has_inj && inj >= rs && inj < re) hit = true; else nfalse++;
+  };
+  int64_t k = 0;
+  while (k < nk) {
+    if (!(row[k] > thresh)) { k++; continue; }
+    int64_t e = k + 1;
+    while (e < nk && row[e] > thresh) e++;
+    const int64_t xs = max((int64_t)0, k - 2), xe = min(nk, e + 2);
+    if (rs >= 0 && xs <= re) re = max(re, xe);
+    else { close_region(); rs = xs; re = xe; }
+    k = e;
+  }
+  close_region();
+  if (has_inj) {
+    const double snr = truth[4 * b + 1];
+    int bin = (int)floor(snr / snr_max * nbins);
+    if (snr == snr_max) bin = nbins - 1;                   // np.histogram: the last edge is inclusive
+    if (bin >= 0 && bin < nbins) {
+      atomicAdd(&injected[bin], 1ULL);
+      if (hit) atomicAdd(&detected[bin], 1ULL);
+    }
+  }
+  if (nfalse) atomicAdd(&counters[0], (unsigned long long)nfalse);
+  if (nreg) atomicAdd(&counters[1], (unsigned long long)nreg);
+}
+
+cudaError_t launch_sweep_score(const double* d_lnO, int B, int64_t nk, int h, const double* d_truth, double thresh,
+                               int nbins, double snr_max, int64_t* d_injected, int64_t* d_detected, int64_t* d_counters,
+                               cudaStream_t s, LaunchStats* st) {
+  k_sweep_score<<<(B + 127) / 128, 128, 0, s>>>(d_lnO, B, nk, h, d_truth, thresh, nbins, snr_max,
+                                                (unsigned long long*)d_injected, (unsigned long long*)d_detected,
+                                                (unsigned long long*)d_counters);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace bfl

@@ -4,8 +4,9 @@ workload of the reference's ``scripts/flare_detection_efficiency.py`` (:399-651;
 Every realisation is an independent light curve, so realisations are sharded across ranks
 (`torchrun`, one process per GPU) with no data-path communication; each rank simulates its block,
 runs the batched detector (noise estimate included) on its GPU, matches detections to injections
-within +-2 samples (script :560-600) and histograms them; the integer counters are summed with one
-all-reduce (NCCL on GPUs).
+within +-2 samples (script :521-612) and histograms them; the integer counters are summed with one
+all-reduce (NCCL on GPUs).  With ``--device-sim`` the simulation (Philox streams per realisation),
+the matching and the histograms run on the device as well and only the counters leave it.
 
     python -m bayesflare_b200.sweep --realisations 10000
     python -m torch.distributed.run --nproc-per-node 8 -m bayesflare_b200.sweep --realisations 10000
@@ -24,7 +25,7 @@ from .lightcurve import Lightcurve
 from .parallel import allreduce_counts, shard_range
 from .synthetic import DT_LONG, simulate_batch
 
-__all__ = ["detection_efficiency", "scripts_detector_kwargs"]
+__all__ = ["detection_efficiency", "scripts_detector_kwargs", "score_host"]
 
 
 def scripts_detector_kwargs(dt=DT_LONG, bglen=55):
@@ -34,49 +35,111 @@ def scripts_detector_kwargs(dt=DT_LONG, bglen=55):
                 noiseimpulseparams={"t0": (0, (bglen - 1) * dt, bglen)})
 
 
+def score_host(lnO, inj_idx, snr, threshold, edges):
+    """The script's bookkeeping for a batch (flare_detection_efficiency.py:521-612) on the host:
+    above-threshold runs expanded by +-2 samples and merged when they touch; the region holding the
+    injection index is a detection, every other region a false positive.  Returns
+    ``(injected, detected, false_alarms, regions)``; ``bfl_sweep_score_dev`` is the device version."""
+    nb, nk = lnO.shape
+    nbins = len(edges) - 1
+    above = lnO > threshold
+    hit = np.zeros(nb, dtype=bool)
+    false_alarms = regions = 0
+    for b in np.nonzero(above.any(axis=1))[0]:
+        d = np.diff(np.concatenate(([0], above[b].astype(np.int8), [0])))
+        starts, stops = np.nonzero(d == 1)[0], np.nonzero(d == -1)[0]
+        rs = re = -1
+        segs = []
+        for a, e in zip(starts, stops):
+            xs, xe = max(a - 2, 0), min(e + 2, nk)
+            if rs >= 0 and xs <= re:
+                re = max(re, xe)
+            else:
+                if rs >= 0:
+                    segs.append((rs, re))
+                rs, re = xs, xe
+        segs.append((rs, re))
+        regions += len(segs)
+        for a, e in segs:
+            if inj_idx[b] >= 0 and a <= inj_idx[b] < e:
+                hit[b] = True
+            else:
+                false_alarms += 1
+    have = inj_idx >= 0
+    injected = np.histogram(snr[have], edges)[0].astype(np.int64)
+    detected = np.histogram(snr[have & hit], edges)[0].astype(np.int64)
+    assert len(injected) == nbins
+    return injected, detected, int(false_alarms), int(regions)
+
+
 def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, snr_max=50., seed=0, sinusoid_amp=0.0,
-                         detector_kwargs=None, batch=2048, rank=0, world=1, device=None, comm_device="cpu", group=None):
+                         detector_kwargs=None, batch=2048, rank=0, world=1, device=None, comm_device="cpu", group=None,
+                         device_sim=False):
     """Run the sweep for the realisations owned by ``rank`` and reduce the counters over ranks.
 
+    ``device_sim=False``: realisations are simulated on the host (NumPy streams seeded per realisation),
+    the detector runs on the device, the bookkeeping on the host.  ``device_sim=True``: everything stays on
+    the device -- simulation (``bfl_sweep_simulate_dev``, counter-based Philox streams per realisation),
+    noise estimate, detector, matching and histograms (``bfl_sweep_score_dev``); only the counters return.
+
     Returns a dict with ``edges`` (SNR bin edges), ``injected`` / ``detected`` (per-bin counts),
-    ``efficiency``, ``false_alarms`` (above-threshold regions away from the injection) and timing."""
+    ``efficiency``, ``false_alarms`` (regions that do not hold the injection) and timing."""
     kw = scripts_detector_kwargs(dt) if detector_kwargs is None else dict(detector_kwargs)
     lo, hi = shard_range(nreal, world, rank)
     edges = np.linspace(0., snr_max, nbins + 1)
     injected = np.zeros(nbins, dtype=np.int64)
     detected = np.zeros(nbins, dtype=np.int64)
     false_alarms = 0
-    det = None
     t_sim = t_gpu = 0.0
     units = 0
-    for first in range(lo, hi, batch):
-        nb = min(batch, hi - first)
+    cts = np.arange(N, dtype=np.float64) * dt
+    det = OddsRatioDetector(Lightcurve(cts=cts, clc=np.zeros(N)), device=device, **kw)
+    h = det.bglen // 2
+    if device_sim and hi > lo:
+        import torch
+        plan = det.plan()
+        ctx = plan.ctx
+        dev = torch.device("cuda", ctx.device if ctx.device >= 0 else torch.cuda.current_device())
+        nbm = min(batch, hi - lo)
+        d_clc = torch.empty((nbm, N), dtype=torch.float64, device=dev)
+        d_truth = torch.empty((nbm, 4), dtype=torch.float64, device=dev)
+        d_sk = torch.empty(nbm, dtype=torch.float64, device=dev)
+        d_lnO = torch.empty((nbm, N - 2 * h), dtype=torch.float64, device=dev)
+        d_inj = torch.zeros(nbins, dtype=torch.int64, device=dev)
+        d_det = torch.zeros(nbins, dtype=torch.int64, device=dev)
+        d_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        spec = det.noise_spec()
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        cts, clc, truth = simulate_batch(nb, N, dt=dt, seed=seed, sinusoid_amp=sinusoid_amp, first=first,
-                                         snr_range=(0., snr_max))
-        t_sim += time.perf_counter() - t0
-        if det is None:
-            det = OddsRatioDetector(Lightcurve(cts=cts, clc=clc[0]), device=device, **kw)
-        t0 = time.perf_counter()
-        lnO = det.oddsratio_batch(clc)                 # [nb, N - 2h], noise sigma estimated on the device
-        t_gpu += time.perf_counter() - t0
-        h = det.bglen // 2
-        units += nb * (N - 2 * h) * det.ngrid_eval
-        above = lnO > threshold
-        idx = truth["idx"] - h
-        near = np.zeros_like(above)
-        cols = np.arange(lnO.shape[1])[None, :]
-        near[:] = np.abs(cols - idx[:, None]) <= 2
-        hit = np.any(above & near, axis=1)
-        injected += np.histogram(truth["snr"], edges)[0]
-        detected += np.histogram(truth["snr"][hit], edges)[0]
-        # false alarms: starts of above-threshold regions that do not touch the injection window
-        starts = above & ~np.concatenate([np.zeros((nb, 1), bool), above[:, :-1]], axis=1)
-        region_id = np.cumsum(starts, axis=1) * above
-        for b in np.nonzero(above.any(axis=1))[0]:
-            ids = np.unique(region_id[b][above[b]])
-            good = np.unique(region_id[b][above[b] & near[b]])
-            false_alarms += len(ids) - len(good)
+        for first in range(lo, hi, batch):
+            nb = min(batch, hi - first)
+            ctx.sweep_simulate_dev(seed, first, nb, N, h, dt, 1.0, sinusoid_amp, 0., snr_max, True,
+                                   d_clc.data_ptr(), d_truth.data_ptr())
+            ctx.noise_sigma_dev(spec, d_clc.data_ptr(), nb, N, d_sk.data_ptr())
+            plan.detector_odds_dev(d_clc.data_ptr(), 0, True, d_sk.data_ptr(), nb, N, 0, N, h, N - h, d_lnO.data_ptr(),
+                                   noisepoly=det.noisepoly)
+            ctx.sweep_score_dev(d_lnO.data_ptr(), nb, N - 2 * h, h, d_truth.data_ptr(), threshold, nbins, snr_max,
+                                d_inj.data_ptr(), d_det.data_ptr(), d_cnt.data_ptr())
+            units += nb * (N - 2 * h) * det.ngrid_eval
+        ctx.sync()
+        t_gpu = time.perf_counter() - t0
+        injected, detected = d_inj.cpu().numpy(), d_det.cpu().numpy()
+        false_alarms = int(d_cnt[0].item())
+    elif hi > lo:
+        for first in range(lo, hi, batch):
+            nb = min(batch, hi - first)
+            t0 = time.perf_counter()
+            _, clc, truth = simulate_batch(nb, N, dt=dt, seed=seed, sinusoid_amp=sinusoid_amp, first=first,
+                                           snr_range=(0., snr_max))
+            t_sim += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            lnO = det.oddsratio_batch(clc)                 # [nb, N - 2h], noise sigma estimated on the device
+            t_gpu += time.perf_counter() - t0
+            units += nb * (N - 2 * h) * det.ngrid_eval
+            inj, dete, fa, _ = score_host(lnO, truth["idx"] - h, truth["snr"], threshold, edges)
+            injected += inj
+            detected += dete
+            false_alarms += fa
     packed = np.concatenate([injected, detected, [false_alarms, units]]).astype(np.int64)
     packed = allreduce_counts(packed, device=comm_device, group=group)
     injected, detected = packed[:nbins], packed[nbins:2 * nbins]
@@ -84,7 +147,7 @@ def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, sn
         eff = detected / injected
     return {"edges": edges, "injected": injected, "detected": detected, "efficiency": eff,
             "false_alarms": int(packed[-2]), "units": int(packed[-1]), "t_simulate_s": t_sim, "t_detector_s": t_gpu,
-            "realisations": int(nreal), "local_realisations": int(hi - lo)}
+            "realisations": int(nreal), "local_realisations": int(hi - lo), "device_sim": bool(device_sim)}
 
 
 def main():
@@ -94,6 +157,7 @@ def main():
     ap.add_argument("--threshold", type=float, default=16.5)
     ap.add_argument("--sinusoid-amp", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--device-sim", action="store_true", help="simulate, match and histogram on the device too")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -108,10 +172,10 @@ def main():
     t0 = time.perf_counter()
     res = detection_efficiency(args.realisations, N=args.samples, threshold=args.threshold, seed=args.seed,
                                sinusoid_amp=args.sinusoid_amp, rank=rank, world=world, device=local_rank,
-                               comm_device=comm_device)
+                               comm_device=comm_device, device_sim=args.device_sim)
     wall = time.perf_counter() - t0
     if rank == 0:
-        out = {"realisations": res["realisations"], "n_gpus": world, "wall_s": wall, "t_detector_s_rank0": res["t_detector_s"],
+        out = {"realisations": res["realisations"], "n_gpus": world, "device_sim": res["device_sim"], "wall_s": wall, "t_detector_s_rank0": res["t_detector_s"],
                "t_simulate_s_rank0": res["t_simulate_s"], "units": res["units"],
                "units_per_s_detector": res["units"] / world / max(res["t_detector_s"], 1e-9) * world,
                "false_alarms": res["false_alarms"],

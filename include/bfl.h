@@ -165,6 +165,26 @@ int bfl_count_regions_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t 
 int bfl_count_regions_total_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh,
                                 int64_t* d_counts, int64_t* d_totals);
 
+/* ---- injection sweep on device (scripts/flare_detection_efficiency.py:399-651; BASELINE config 5) ----
+ * bfl_sweep_simulate_dev: B light curves of N <= 8192 samples, realisation indices first .. first+B-1 (the
+ *   stream of a realisation depends on (seed, index) only -- counter-based Philox -- so a sweep sharded over
+ *   ranks simulates the same curves whatever the number of ranks): white noise of standard deviation nstd,
+ *   optional sinusoid (amplitude U[0, sinusoid_amp] nstd, period 2..31 d), one injected flare (script :321-335:
+ *   tau_exp U[1800, 10800], tau_gauss U[0, 5400] redrawn until <= tau_exp, index randint(halfwin, N-halfwin-1),
+ *   signal-to-noise U[snr_lo, snr_hi]) when inject != 0, median removed (data.py:271-277).
+ *   d_clc dev [B][N] out; d_truth dev [B][4] out: injection index (or -1), snr, tau_gauss, tau_exp.
+ * bfl_sweep_score_dev: above-threshold runs of d_lnO[B][nk] (edge-trimmed by halfwin) expanded by +-2 samples
+ *   and merged (script :521-580); the region holding the injection is a detection, every other one a false
+ *   positive (:586-612).  ACCUMULATES (arrays not cleared): d_injected / d_detected [nbins] histograms over
+ *   signal-to-noise in [0, snr_max] as np.histogram bins them, d_counters[2] = {false positives, regions}.
+ * Both asynchronous on the context's stream.                                                            */
+int bfl_sweep_simulate_dev(bfl_ctx* ctx, uint64_t seed, int64_t first, int32_t B, int32_t N, int32_t halfwin, double dt,
+                           double nstd, double sinusoid_amp, double snr_lo, double snr_hi, int32_t inject, double* d_clc,
+                           double* d_truth);
+int bfl_sweep_score_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t nk, int32_t halfwin, const double* d_truth,
+                        double thresh, int32_t nbins, double snr_max, int64_t* d_injected, int64_t* d_detected,
+                        int64_t* d_counters);
+
 /* ---- OddsRatioDetector.thresholder (find.py:915-1019) on device ----------------------
  * contiguous regions of lnO > thresh, expanded by `expand` and merged; per region the
  * maximum and its index.  lnO host [n]; segs host [max_segs][2] (start, stop), maxval /

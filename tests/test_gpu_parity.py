@@ -644,3 +644,73 @@ def test_widest_window_and_fully_masked_grid(monkeypatch):
     assert np.all(Bm.lnBmargAmp == -np.inf)
     refm, rr = orc.bayes_factors(clc, np.zeros(N), ts, "flare", prm, 0.98)
     assert np.all(refm == -np.inf)
+
+
+@pytest.mark.gpu
+def test_sweep_on_device_simulation_scoring_and_statistics():
+    """(i) the device bookkeeping kernel equals the host restatement of the script's
+    segment logic on the same log odds; (ii) device-simulated curves have the statistics asked for
+    (unit white noise, median removed, injected flare at the recorded index with the recorded SNR);
+    (iii) the all-device sweep is independent of the sharding and agrees with the host-simulated sweep
+    within counting errors."""
+    import torch
+    from bayesflare_b200.sweep import detection_efficiency, score_host
+    from bayesflare_b200.synthetic import simulate_batch
+    ctx = _lib.default_context()
+    N, h, nb = 1639, 27, 300
+    # (i) scoring
+    cts, clc, truth = simulate_batch(nb, N, seed=9)
+    truth["idx"][:5] = -1 + 0 * truth["idx"][:5]            # a few curves without an injection record
+    det = bf.OddsRatioDetector(_lc(cts, clc[0]), noiseestmethod="tailveto")
+    lnO = det.oddsratio_batch(clc)
+    edges = np.linspace(0., 50., 51)
+    inj_trim = np.where(truth["idx"] >= 0, truth["idx"] - h, -1)
+    want = score_host(lnO, inj_trim, truth["snr"], 5.0, edges)     # low threshold: many regions and false alarms
+    tr = np.stack([np.where(truth["idx"] >= 0, truth["idx"], -1).astype(float), truth["snr"], truth["taugauss"], truth["tauexp"]], axis=1)
+    d_lnO, d_tr = torch.from_numpy(lnO).cuda(), torch.from_numpy(tr).cuda()
+    d_inj = torch.zeros(50, dtype=torch.int64, device="cuda"); d_det = torch.zeros_like(d_inj)
+    d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.sweep_score_dev(d_lnO.data_ptr(), nb, N - 2 * h, h, d_tr.data_ptr(), 5.0, 50, 50., d_inj.data_ptr(), d_det.data_ptr(), d_cnt.data_ptr())
+    ctx.sync()
+    np.testing.assert_array_equal(d_inj.cpu().numpy(), want[0])
+    np.testing.assert_array_equal(d_det.cpu().numpy(), want[1])
+    assert d_cnt.cpu().tolist() == [want[2], want[3]] and want[2] > 10
+    # (ii) simulation
+    B = 512
+    d_clc = torch.empty((B, N), dtype=torch.float64, device="cuda"); d_t = torch.empty((B, 4), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.sweep_simulate_dev(123, 1000, B, N, h, DT, 1.0, 0.0, 0., 50., True, d_clc.data_ptr(), d_t.data_ptr())
+    ctx.sync()
+    x, t = d_clc.cpu().numpy(), d_t.cpu().numpy()
+    assert np.all(np.isfinite(x)) and np.allclose(np.median(x, axis=1), 0.0, atol=1e-12)
+    idx, snr, tg, te = t[:, 0].astype(int), t[:, 1], t[:, 2], t[:, 3]
+    assert idx.min() >= h and idx.max() <= N - h - 2 and np.all(tg <= te) and np.all((te >= 1800) & (te <= 10800))
+    assert 20 < snr.mean() < 30 and snr.min() >= 0 and snr.max() <= 50
+    ts = np.arange(N) * DT
+    for b in (0, 17, 300):                                   # remove the recorded injection: unit white noise remains
+        m = orc.flare_model(ts, ts[idx[b]], 1.0, tg[b], te[b])
+        lo, hi = max(0, idx[b] - 4 * h), min(N, idx[b] + 12 * h)
+        m[:lo] = 0; m[hi:] = 0
+        resid = x[b] - m * snr[b] / np.sqrt(np.sum(m ** 2))
+        assert abs(np.std(resid) - 1.0) < 0.08 and abs(np.mean(resid - np.median(resid))) < 0.1
+    noise = x[snr < 1.0]
+    if len(noise):
+        assert abs(np.std(noise) - 1.0) < 0.05
+    ctx.sweep_simulate_dev(123, 1100, 8, N, h, DT, 1.0, 0.0, 0., 50., True, d_clc.data_ptr(), d_t.data_ptr())   # realisation 1100.. again
+    ctx.sync()
+    np.testing.assert_array_equal(d_clc[:8].cpu().numpy(), x[100:108])      # streams depend on (seed, index) only
+    # (iii) all-device sweep
+    whole = detection_efficiency(3000, N=N, seed=4, batch=1024, device_sim=True)
+    assert whole["injected"].sum() == 3000 and np.all(whole["detected"] <= whole["injected"])
+    parts = [detection_efficiency(3000, N=N, seed=4, batch=512, rank=r, world=3, device_sim=True) for r in range(3)]
+    np.testing.assert_array_equal(sum(p["injected"] for p in parts), whole["injected"])
+    np.testing.assert_array_equal(sum(p["detected"] for p in parts), whole["detected"])
+    assert sum(p["false_alarms"] for p in parts) == whole["false_alarms"]
+    host = detection_efficiency(3000, N=N, seed=4, batch=1024)
+    eff_d = whole["detected"][20:].sum() / whole["injected"][20:].sum()
+    eff_h = host["detected"][20:].sum() / host["injected"][20:].sum()
+    assert eff_d > 0.97 and abs(eff_d - eff_h) < 0.02
+    mid_d = whole["detected"][5:15].sum() / whole["injected"][5:15].sum()
+    mid_h = host["detected"][5:15].sum() / host["injected"][5:15].sum()
+    assert abs(mid_d - mid_h) < 0.08                         # transition region: binomial scatter of ~600 curves
