@@ -2758,45 +2758,57 @@ __global__ void __launch_bounds__(256) k_tv_hist(const double* __restrict__ d, i
   }
 }
 
-// part 2 (one thread per curve, sequential like np.cumsum): density, cumulative distribution,
-// np.unique + scipy interp1d at 0.5 -/+ cp/2 (noise.py:83-101)
-__global__ void k_tv_finish(const int* __restrict__ counts, const double* __restrict__ range, int64_t N, int B,
-                            double sigma, double cp, double* __restrict__ sk) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// part 2 (one WARP per curve): density, cumulative distribution, np.unique + scipy interp1d at
+// 0.5 -/+ cp/2 (noise.py:83-101).  The cumulative sum must run in np.cumsum's order (the unique test compares
+// consecutive sums for equality), so it stays sequential -- but everything that does not depend on the running
+// sum (bin edges, the two divisions of the density, the bin centre) is computed by the 32 lanes for 32 bins at
+// a time with coalesced loads, and the serial part is one shuffle + one add per bin, the same in every lane.
+__global__ void __launch_bounds__(128) k_tv_finish(const int* __restrict__ counts, const double* __restrict__ range,
+                                                   int64_t N, int B, double sigma, double cp, double* __restrict__ sk) {
+  const int b = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const double lo = range[2 * b], hi = range[2 * b + 1];
-  if (isnan(lo)) { sk[b] = nan(""); return; }
+  if (isnan(lo)) { if (lane == 0) sk[b] = nan(""); return; }
   const int* c = counts + (size_t)b * N;
   const double step = (hi - lo) / (double)N;
   const double w0 = tv_edge(1, N, lo, hi, step) - tv_edge(0, N, lo, hi, step);
   const double tgt[2] = {0.5 - cp / 2.0, 0.5 + cp / 2.0};
   double val[2] = {nan(""), nan("")};
-  int state[2] = {0, 0};            // 0 searching, 1 waiting for the second unique point, 2 done
+  int state[2] = {0, 0};            // 0 searching, 1 waiting for the second unique point, 2 done, 3 out of range
   double cs = 0.0, xl = 0.0, yl = 0.0, xp = 0.0, yp = 0.0;
   int nu = 0;
-  double e0 = tv_edge(0, N, lo, hi, step);
-  for (int64_t i = 0; i < N; i++) {
-    const double e1 = tv_edge(i + 1, N, lo, hi, step);
-    const double ni = __ddiv_rn(__ddiv_rn((double)c[i], e1 - e0), (double)N);   // n / db / n.sum()
-    cs = __dadd_rn(cs, __dmul_rn(ni, w0));
-    if (nu == 0 || cs != xl) {       // a new unique value of the cumulative distribution (first index kept)
-      xp = xl; yp = yl;
-      xl = cs; yl = (e0 + e1) / 2.0;
-      nu++;
+  for (int64_t base = 0; base < N; base += 32) {
+    const int64_t i = base + lane;
+    double term = 0.0, ymid = 0.0;
+    if (i < N) {
+      const double e0 = tv_edge(i, N, lo, hi, step), e1 = tv_edge(i + 1, N, lo, hi, step);
+      const double ni = __ddiv_rn(__ddiv_rn((double)c[i], e1 - e0), (double)N);   // n / db / n.sum()
+      term = __dmul_rn(ni, w0);
+      ymid = (e0 + e1) / 2.0;
+    }
+    const int cnt = (int)min((int64_t)32, N - base);
+    for (int t = 0; t < cnt; t++) {
+      cs = __dadd_rn(cs, __shfl_sync(0xffffffffu, term, t));
+      if (nu == 0 || cs != xl) {       // a new unique value of the cumulative distribution (first index kept)
+        xp = xl; yp = yl;
+        xl = cs; yl = __shfl_sync(0xffffffffu, ymid, t);
+        nu++;
 #pragma unroll
-      for (int t = 0; t < 2; t++) {
-        if (state[t] == 1) {           // target sits at/below the first point: interpolate on points 0 and 1
-          val[t] = (yl - yp) / (xl - xp) * (tgt[t] - xp) + yp;
-          state[t] = 2;
-        } else if (state[t] == 0 && xl >= tgt[t]) {
-          if (nu == 1) state[t] = (tgt[t] < xl) ? 3 : 1;     // below the interpolation range -> error
-          else { val[t] = (yl - yp) / (xl - xp) * (tgt[t] - xp) + yp; state[t] = 2; }
+        for (int q = 0; q < 2; q++) {
+          if (state[q] == 1) {           // target sits at/below the first point: interpolate on points 0 and 1
+            val[q] = (yl - yp) / (xl - xp) * (tgt[q] - xp) + yp;
+            state[q] = 2;
+          } else if (state[q] == 0 && xl >= tgt[q]) {
+            if (nu == 1) state[q] = (tgt[q] < xl) ? 3 : 1;     // below the interpolation range -> error
+            else { val[q] = (yl - yp) / (xl - xp) * (tgt[q] - xp) + yp; state[q] = 2; }
+          }
         }
       }
     }
-    e0 = e1;
+    if (state[0] >= 2 && state[1] >= 2) break;      // both quantiles settled (warp-uniform)
   }
-  sk[b] = (state[0] == 2 && state[1] == 2) ? (val[1] - val[0]) / (2.0 * sigma) : nan("");
+  if (lane == 0) sk[b] = (state[0] == 2 && state[1] == 2) ? (val[1] - val[0]) / (2.0 * sigma) : nan("");
 }
 
 cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
@@ -2822,7 +2834,7 @@ cudaError_t launch_tv_sigma(const double* d_resid, int64_t N, int B, double sigm
   if (e != cudaSuccess) return e;
   k_tv_hist<<<B, 256, 0, s>>>(d_resid, N, d_counts, d_range);
   st->launches++;
-  k_tv_finish<<<(B + 31) / 32, 32, 0, s>>>(d_counts, d_range, N, B, sigma, erf(sigma / sqrt(2.0)), d_sk);
+  k_tv_finish<<<(B + 3) / 4, 128, 0, s>>>(d_counts, d_range, N, B, sigma, erf(sigma / sqrt(2.0)), d_sk);
   st->launches++;
   return cudaGetLastError();
 }
@@ -2996,36 +3008,62 @@ cudaError_t launch_sweep_simulate(unsigned long long seed, long long first, int 
   return cudaGetLastError();
 }
 
-// One thread per curve: above-threshold runs expanded by +-2 samples and merged when they touch
+// One warp per curve: above-threshold runs expanded by +-2 samples and merged when they touch
 // (flare_detection_efficiency.py:521-580); the region holding the injection index is a detection, every
 // other region a false positive (:586-612).  Histograms over signal-to-noise ratio as np.histogram.
-__global__ void k_sweep_score(const double* __restrict__ lnO, int B, int64_t nk, int h, const double* __restrict__ truth,
-                              double thresh, int nbins, double snr_max, unsigned long long* injected,
-                              unsigned long long* detected, unsigned long long* counters) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// The warp reads 32 samples at a time (coalesced) and ballots them into a bit mask; the run/region state
+// machine works on the masks with bit scans (uniform in every lane), so noise-only stretches cost one
+// load and one ballot per 32 samples.
+__global__ void __launch_bounds__(128) k_sweep_score(const double* __restrict__ lnO, int B, int64_t nk, int h,
+                                                     const double* __restrict__ truth, double thresh, int nbins,
+                                                     double snr_max, unsigned long long* injected,
+                                                     unsigned long long* detected, unsigned long long* counters) {
+  const int b = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
   if (b >= B) return;
   const double* row = lnO + (size_t)b * nk;
   const int64_t inj = (int64_t)truth[4 * b] - h;           // injection index in the edge-trimmed series
   const bool has_inj = truth[4 * b] >= 0.0;
-  int64_t rs = -1, re = -1;
+  int64_t rs = -1, re = -1, run_start = 0;
   int nfalse = 0, nreg = 0;
-  bool hit = false;
+  bool hit = false, in_run = false;
   auto close_region = [&]() {
     if (rs < 0) return;
     nreg++;
     if (has_inj && inj >= rs && inj < re) hit = true; else nfalse++;
   };
-  int64_t k = 0;
-  while (k < nk) {
-    if (!(row[k] > thresh)) { k++; continue; }
-    int64_t e = k + 1;
-    while (e < nk && row[e] > thresh) e++;
-    const int64_t xs = max((int64_t)0, k - 2), xe = min(nk, e + 2);
+  auto emit_run = [&](int64_t a, int64_t e) {              // above-threshold run [a, e)
+    const int64_t xs = max((int64_t)0, a - 2), xe = min(nk, e + 2);
     if (rs >= 0 && xs <= re) re = max(re, xe);
     else { close_region(); rs = xs; re = xe; }
-    k = e;
+  };
+  for (int64_t kb = 0; kb < nk; kb += 32) {
+    const int64_t k = kb + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, k < nk && row[k] > thresh);
+    if (m == 0u && !in_run) continue;
+    int pos = 0;
+    while (pos < 32) {
+      const unsigned from = (pos == 0) ? 0xffffffffu : (0xffffffffu << pos);
+      if (in_run) {
+        const unsigned z = ~m & from;
+        if (z == 0u) break;                                // the run continues into the next chunk
+        const int q = __ffs(z) - 1;
+        emit_run(run_start, kb + q);
+        in_run = false;
+        pos = q + 1;
+      } else {
+        const unsigned o = m & from;
+        if (o == 0u) break;
+        const int q = __ffs(o) - 1;
+        run_start = kb + q;
+        in_run = true;
+        pos = q + 1;
+      }
+    }
   }
+  if (in_run) emit_run(run_start, nk);
   close_region();
+  if (lane != 0) return;
   if (has_inj) {
     const double snr = truth[4 * b + 1];
     int bin = (int)floor(snr / snr_max * nbins);
@@ -3042,7 +3080,7 @@ __global__ void k_sweep_score(const double* __restrict__ lnO, int B, int64_t nk,
 cudaError_t launch_sweep_score(const double* d_lnO, int B, int64_t nk, int h, const double* d_truth, double thresh,
                                int nbins, double snr_max, int64_t* d_injected, int64_t* d_detected, int64_t* d_counters,
                                cudaStream_t s, LaunchStats* st) {
-  k_sweep_score<<<(B + 127) / 128, 128, 0, s>>>(d_lnO, B, nk, h, d_truth, thresh, nbins, snr_max,
+  k_sweep_score<<<(B + 3) / 4, 128, 0, s>>>(d_lnO, B, nk, h, d_truth, thresh, nbins, snr_max,
                                                 (unsigned long long*)d_injected, (unsigned long long*)d_detected,
                                                 (unsigned long long*)d_counters);
   st->launches++;

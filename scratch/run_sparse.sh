@@ -1,0 +1,5 @@
+python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -4
+BFL_NO_SPARSE=1 python tools/time_window.py 2>&1 | tail -1
+python tools/time_window.py 2>&1 | tail -1
+python -m bayesflare_b200.sweep --realisations 100000 --device-sim 2>/dev/null | tail -1 | cut -c1-260
+BFL_NO_SPARSE=1 python -m bayesflare_b200.sweep --realisations 100000 --device-sim 2>/dev/null | tail -1 | cut -c1-260
