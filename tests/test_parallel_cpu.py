@@ -91,3 +91,24 @@ def test_single_process_is_a_no_op():
     rec = np.arange(10.0).reshape(2, 5)
     np.testing.assert_array_equal(parallel.gather_detections(rec), rec)
     np.testing.assert_array_equal(parallel.allreduce_counts([1, 2, 3]), [1, 2, 3])
+
+
+def test_sweep_bookkeeping_matches_the_scripts_rules():
+    """scripts/flare_detection_efficiency.py:521-612 on hand-made log odds: runs are expanded by +-2 samples
+    and merged when they touch; the region holding the injection is the detection, the rest false positives"""
+    import numpy as np
+    from bayesflare_b200.sweep import score_host
+    nk = 60
+    lnO = np.full((5, nk), -1.0)
+    lnO[0, 10:13] = 20.          # one run; injection at 14 -> inside the expanded region [8, 15)
+    lnO[1, 10:13] = 20.          # injection at 15 -> just outside: a false positive, no detection
+    lnO[2, 10:12] = 20.; lnO[2, 16:18] = 20.     # [8,14) and [14,20) touch -> ONE region holding 18
+    lnO[3, 0] = 20.; lnO[3, nk - 1] = 20.; lnO[3, 30] = 20.      # clamped at the ends; injection at 30
+    lnO[4, 5] = 20.              # no injection recorded: always a false positive
+    inj = np.array([14, 15, 18, 30, -1])
+    snr = np.array([5., 15., 25., 50., 35.])
+    edges = np.linspace(0., 50., 6)
+    injected, detected, fa, regions = score_host(lnO, inj, snr, 16.5, edges)
+    assert injected.tolist() == [1, 1, 1, 0, 1]      # 50.0 falls in the last (inclusive) bin; curve 4 not injected
+    assert detected.tolist() == [1, 0, 1, 0, 1]
+    assert fa == 1 + 0 + 2 + 1 and regions == 1 + 1 + 1 + 3 + 1
