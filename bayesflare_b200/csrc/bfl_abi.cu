@@ -42,8 +42,6 @@ struct bfl_ctx {
   LaunchStats stats;
   bool timing = false;
   cudaStream_t s_in = nullptr, s_out = nullptr;           // copy streams of the pipelined host entry point
-  cudaStream_t s_aux = nullptr;                            // epilogue stream of the overlapped split form
-  std::vector<cudaEvent_t> aux_ev;
   std::vector<cudaEvent_t> pipe_ev;                        // cached events for it
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tfree; // recycled event pairs
@@ -121,8 +119,6 @@ int bfl_ctx_destroy(bfl_ctx* c) {
     if (kv.second.first) cudaFree(kv.second.first);
   for (auto& kv : c->fft) cufftDestroy(kv.second);
   for (auto ev : c->pipe_ev) cudaEventDestroy(ev);
-  for (auto ev : c->aux_ev) cudaEventDestroy(ev);
-  if (c->s_aux) cudaStreamDestroy(c->s_aux);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -506,19 +502,8 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;
   if ((rc = c->get("halflogv", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.halflogv = (double*)ptr;
   if ((rc = c->get("uconst", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.uconst = (double*)ptr;
-  sc.ncounters = std::max(sc.NC, 16);
-  if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)sc.ncounters, &ptr))) return rc;
+  if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)sc.NC, &ptr))) return rc;
   sc.tile_counters = (unsigned long long*)ptr;
-  sc.aux_stream = nullptr; sc.aux_events = nullptr; sc.naux_events = 0;
-  if (sc.Y) {
-    if (!c->s_aux) CK(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-    while (c->aux_ev.size() < 17) {
-      cudaEvent_t ev;
-      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      c->aux_ev.push_back(ev);
-    }
-    sc.aux_stream = c->s_aux; sc.aux_events = c->aux_ev.data(); sc.naux_events = (int)c->aux_ev.size();
-  }
   sc.dw = sc.uu = nullptr;
   if (need_general) {
     if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
@@ -716,16 +701,8 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
   // Sub-batch sizes 1:3:3:1 -- small first and last pieces keep the exposed copy-in / copy-out short,
   // large middle pieces keep the kernel's tail (one ~100 us warp tile) a small fraction of its run.
   int nsub = 1;
-  std::vector<int> weights;
-  if (!out_marg && B >= 512) {
-    weights = {1, 3, 3, 1};
-    if (const char* e = getenv("BFL_PIPE")) {            // experiment knob: e.g. BFL_PIPE=1,2,2,2,1
-      std::vector<int> w;
-      for (const char* q = e; *q;) { w.push_back(std::max(1, atoi(q))); while (*q && *q != ',') q++; if (*q == ',') q++; }
-      if (w.size() >= 2 && w.size() <= 16) weights = w;
-    }
-    nsub = (int)weights.size();
-  } else if (!out_marg && B >= 256) { weights = {1, 1}; nsub = 2; }
+  if (!out_marg && B >= 512) nsub = 4;
+  else if (!out_marg && B >= 256) nsub = 2;
   if (nsub > 1) {
     if (!c->s_in) CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     if (!c->s_out) CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -739,12 +716,8 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
     CK(cudaEventRecord(c->pipe_ev[2 * nsub], s));
     CK(cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * nsub], 0));   // previous users of the input buffers are done
     std::vector<int> lo(nsub + 1);
-    {
-      int wsum = 0, acc = 0;
-      for (int w : weights) wsum += w;
-      lo[0] = 0;
-      for (int j = 0; j < nsub; j++) { acc += weights[j]; lo[j + 1] = (int)((int64_t)B * acc / wsum); }
-    }
+    if (nsub == 4) { lo[0] = 0; lo[1] = B / 8; lo[2] = B / 2; lo[3] = B - B / 8; lo[4] = B; }
+    else for (int j = 0; j <= nsub; j++) lo[j] = (int)((int64_t)B * j / nsub);
     for (int j = 0; j < nsub; j++) {
       const size_t off = (size_t)lo[j] * N, cnt = (size_t)(lo[j + 1] - lo[j]) * N;
       CK(cudaMemcpyAsync((double*)d_clc + off, clc + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->s_in));

@@ -374,8 +374,8 @@ __global__ void k_prep_whiten(const double* __restrict__ clc, const double* __re
 }
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st) {
-  k_prep_scalars<<<(std::max(sv.B, std::max(sc.NC, sc.ncounters)) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
-                                                                   sc.uconst, sc.tile_counters, std::max(sc.NC, sc.ncounters));
+  k_prep_scalars<<<(std::max(sv.B, sc.NC) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
+                                                                   sc.uconst, sc.tile_counters, sc.NC);
   st->launches++;
   if (need_general) {
     const int64_t n = sv.seglen * sv.B;
@@ -1032,51 +1032,20 @@ bool fast_split_fits(const PlanView& pv) {
          epi_smem_bytes(pv.G, pv.S, epi_arows(pv), BFL_EPI_SPT) <= 50 * 1024 * BFL_EPI_SPT;   // wsep_ok: templates grouped by B shape
 }
 
-// mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds.
-// Large fused batches are cut into chunks of curves: the correlation of chunk c+1 runs on the context's
-// stream while the epilogue of chunk c runs on the auxiliary stream.  The two kernels stress different
-// resources (the correlation saturates the FP64 pipe with few fat warps, the epilogue is a long dependent
-// chain per sample that leaves the pipe half idle), so their CTAs are sized to be co-resident on every SM
-// (1 correlation CTA + 2 epilogue CTAs) and fill each other's stalls; a chunk's Y (about the size of L2)
-// is consumed right after it is produced.
-static int split_chunks(const SeriesView& sv, const Scratch& sc, int mode) {
-  static int off = -1, force = 0;
-  if (off < 0) {
-    const char* e = getenv("BFL_OVERLAP"); off = (e && atoi(e)) ? 0 : 1;   // measured slower than back-to-back: off unless asked for
-    if (const char* f = getenv("BFL_CHUNKS")) force = atoi(f);
-  }
-  if (off || mode != 2 || !sc.aux_stream || sv.B < 128) return 1;
-  int n = force > 0 ? force : 8;
-  n = std::min(n, sv.B / 64);
-  n = std::min(n, std::min(sc.naux_events - 1, sc.ncounters));
-  return std::max(n, 1);
-}
-
+// mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
 cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
                                 double* d_lnO, cudaStream_t s, LaunchStats* st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int64_t nk = sv.k1 - sv.k0;
   const int KT = sc.KT;
-  const int nchunk = split_chunks(sv, sc, mode);
-  const bool overlap = nchunk > 1;
-  static int ov_cap_c = -1, ov_cap_e = -1;
-  if (ov_cap_c < 0) { const char* e1 = getenv("BFL_OV_CAPC"); ov_cap_c = e1 ? atoi(e1) : 1; const char* e2 = getenv("BFL_OV_CAPE"); ov_cap_e = e2 ? atoi(e2) : 2; }
-  constexpr int SPT = BFL_EPI_SPT;
+  CorrArgs c;
+  c.data = sv.clc; c.sqrtu = sc.sqrtu; c.seglen = sv.seglen; c.N = sv.N; c.seg0 = sv.seg0; c.k0 = sv.k0; c.k1 = sv.k1;
+  c.B = sv.B; c.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
+  c.total_wtiles = (int64_t)c.tiles_per_curve * sv.B; c.tile_counter = sc.tile_counters;
+  c.shapes = pv.shapes; c.S = pv.S; c.WP = pv.WP; c.Y = sc.Y;
   const size_t smem1 = corr_smem_bytes(pv.S, KT);
-  const int arows = epi_arows(pv);
-  const size_t smem2 = epi_smem_bytes(pv.G, pv.S, arows, SPT);
   cudaError_t e;
-  for (int ch = 0; ch < nchunk; ch++) {
-    const int b0 = (int)((int64_t)sv.B * ch / nchunk), b1 = (int)((int64_t)sv.B * (ch + 1) / nchunk);
-    const int Bc = b1 - b0;
-    double* Yc = sc.Y + (size_t)pv.S * (size_t)b0 * nk;
-    CorrArgs c;
-    c.data = sv.clc + (size_t)b0 * sv.seglen; c.sqrtu = sc.sqrtu + b0;
-    c.seglen = sv.seglen; c.N = sv.N; c.seg0 = sv.seg0; c.k0 = sv.k0; c.k1 = sv.k1;
-    c.B = Bc; c.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
-    c.total_wtiles = (int64_t)c.tiles_per_curve * Bc; c.tile_counter = sc.tile_counters + ch;
-    c.shapes = pv.shapes; c.S = pv.S; c.WP = pv.WP; c.Y = Yc;
 #define BFL_CORR(KT_)                                                                                       \
   do {                                                                                                      \
     e = cudaFuncSetAttribute(k_corr_shapes<KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);  \
@@ -1084,33 +1053,29 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
     int occ = 1;                                                                                            \
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_corr_shapes<KT_>, FAST_TPB, smem1);           \
     if (e != cudaSuccess) return e;                                                                         \
-    if (overlap && ov_cap_c > 0) occ = std::min(occ, ov_cap_c);                                             \
     int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);                                                        \
     const int64_t need = (c.total_wtiles + FAST_TPB / 32 - 1) / (FAST_TPB / 32);                            \
     if (gx > need) gx = need;                                                                               \
     k_corr_shapes<KT_><<<(unsigned)(gx < 1 ? 1 : gx), FAST_TPB, smem1, s>>>(c);                             \
   } while (0)
-    if (KT == 4) BFL_CORR(4); else if (KT == 2) BFL_CORR(2); else BFL_CORR(1);
+  if (KT == 4) BFL_CORR(4); else if (KT == 2) BFL_CORR(2); else BFL_CORR(1);
 #undef BFL_CORR
-    st->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    cudaStream_t se = s;
-    if (overlap) {
-      se = sc.aux_stream;
-      if ((e = cudaEventRecord(sc.aux_events[ch], s)) != cudaSuccess) return e;
-      if ((e = cudaStreamWaitEvent(se, sc.aux_events[ch], 0)) != cudaSuccess) return e;
-    }
-    EpiArgs a;
-    a.Y = Yc; a.halflogv = sc.halflogv + b0; a.nk = nk; a.BK = (int64_t)Bc * nk; a.N = sv.N; a.k0 = sv.k0;
-    a.B = Bc; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
-    for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
-    for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
-    for (int h = 0; h < pv.nhyp; h++) { a.hyp_B0[h] = pv.hyp_B0[h]; a.hyp_nB[h] = pv.hyp_nB[h]; }
-    a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
-    a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = arows;
-    a.noisepoly = noisepoly; a.lnO = d_lnO ? d_lnO + (size_t)b0 * nk : nullptr; a.part = sc.part;
-    const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
+  st->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+
+  EpiArgs a;
+  a.Y = sc.Y; a.halflogv = sc.halflogv; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
+  a.B = sv.B; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
+  for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
+  for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
+  for (int h = 0; h < pv.nhyp; h++) { a.hyp_B0[h] = pv.hyp_B0[h]; a.hyp_nB[h] = pv.hyp_nB[h]; }
+  a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = epi_arows(pv);
+  a.noisepoly = noisepoly; a.lnO = d_lnO; a.part = sc.part;
+  constexpr int SPT = BFL_EPI_SPT;
+  const size_t smem2 = epi_smem_bytes(pv.G, pv.S, a.arows, SPT);
+  const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
 #define BFL_EPI(MODE_)                                                                                      \
   do {                                                                                                      \
     e = cudaFuncSetAttribute(k_epilogue<MODE_, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
@@ -1118,22 +1083,14 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
     int occ = 1;                                                                                            \
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_epilogue<MODE_, SPT>, EPI_TPB, smem2);        \
     if (e != cudaSuccess) return e;                                                                         \
-    if (overlap && ov_cap_e > 0) occ = std::min(occ, ov_cap_e);                                             \
     int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);                                                        \
     if (gx > ntiles) gx = ntiles;                                                                           \
-    k_epilogue<MODE_, SPT><<<(unsigned)(gx < 1 ? 1 : gx), EPI_TPB, smem2, se>>>(a);                         \
+    k_epilogue<MODE_, SPT><<<(unsigned)(gx < 1 ? 1 : gx), EPI_TPB, smem2, s>>>(a);                          \
   } while (0)
-    if (mode == 2) BFL_EPI(2); else BFL_EPI(0);
+  if (mode == 2) BFL_EPI(2); else BFL_EPI(0);
 #undef BFL_EPI
-    st->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  if (overlap) {   // later work on the context's stream is ordered after the last epilogue
-    if ((e = cudaEventRecord(sc.aux_events[nchunk], sc.aux_stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamWaitEvent(s, sc.aux_events[nchunk], 0)) != cudaSuccess) return e;
-  }
-  return cudaSuccess;
+  st->launches++;
+  return cudaGetLastError();
 }
 
 size_t fast_smem_bytes(int W, int gchunk, int KT) {

@@ -82,12 +82,6 @@ struct Scratch {
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
   int sub;         // partials per template chunk: 2 when the warp-specialised kernel runs, else 1
-  // split form, overlapped: the batch is cut into curve chunks; k_corr_shapes of chunk c+1 (context stream)
-  // runs concurrently with k_epilogue of chunk c (auxiliary stream).  Provided by the context.
-  cudaStream_t aux_stream;
-  cudaEvent_t* aux_events;   // [naux_events]
-  int naux_events;
-  int ncounters;             // tile counters available (>= NC, >= chunks)
 };
 
 struct LaunchStats { int64_t launches = 0; };
