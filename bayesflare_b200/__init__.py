@@ -11,7 +11,8 @@ by hand-written CUDA kernels behind the C ABI in ``include/bfl.h``.  There is no
 """
 from .lightcurve import Lightcurve
 from .models import Model, Flare, Transit, Expdecay, Impulse, Gaussian, Step, ModelCurve
-from .noise import estimate_noise_ps, estimate_noise_tv, savitzky_golay, nextpow2
+from .noise import (estimate_noise_ps, estimate_noise_tv, savitzky_golay, nextpow2, running_median,
+                    highpass_filter_lightcurve)
 from .general import logplus, logminus, logtrapz
 from .bayes import Bayes, ParameterEstimationGrid
 from .finder import OddsRatioDetector, contiguous_regions
@@ -21,6 +22,7 @@ from . import fitsio
 __version__ = "0.1.0"
 
 __all__ = ["Lightcurve", "Model", "Flare", "Transit", "Expdecay", "Impulse", "Gaussian", "Step", "ModelCurve",
-           "estimate_noise_ps", "estimate_noise_tv", "savitzky_golay", "nextpow2", "logplus", "logminus",
+           "estimate_noise_ps", "estimate_noise_tv", "savitzky_golay", "nextpow2", "running_median",
+           "highpass_filter_lightcurve", "logplus", "logminus",
            "logtrapz", "Bayes", "ParameterEstimationGrid", "OddsRatioDetector", "contiguous_regions",
            "flare_search", "merge_results", "write_result", "fitsio"]

@@ -141,8 +141,7 @@ class Lightcurve:
         self.detrend_knee = knee
 
     def detrend(self, method='none', nbins=None, order=None, knee=None):
-        """data.py:377-424 (Savitzky-Golay; the running-median and Butterworth detrenders are
-        not on the odds-ratio path)."""
+        """data.py:377-424: Savitzky-Golay (the odds-ratio path), running median, Butterworth high-pass."""
         from .noise import savitzky_golay
         self.set_detrend(method=method, nbins=nbins, order=order, knee=knee)
         self.detrended = True
@@ -153,7 +152,19 @@ class Lightcurve:
             ffit = savitzky_golay(self.clc, nbins, order)
             self.clc = self.clc - ffit
             self.detrend_fit = np.copy(ffit)
-        elif method in ('runningmedian', 'highpassfilter'):
-            raise NotImplementedError("detrend method '%s' is outside the odds-ratio hot path" % method)
+        elif method == 'runningmedian':
+            if nbins is None:
+                raise ValueError("Number of bins for running median filter not set")
+            from .noise import running_median
+            ffit = running_median(self.clc, nbins)
+            self.clc = self.clc - ffit
+            self.detrend_fit = np.copy(ffit)
+        elif method == 'highpassfilter':
+            if knee is None:
+                raise ValueError("Knee frequency for high-pass filter not set.")
+            from .noise import highpass_filter_lightcurve
+            # the reference reads ``.clc`` of the returned ndarray here (data.py:421-422) and cannot run;
+            # the filtered series is what it means
+            self.clc = np.copy(highpass_filter_lightcurve(self, knee=knee))
         else:
             raise ValueError("No detrend method set")

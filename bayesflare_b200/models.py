@@ -80,11 +80,15 @@ class Model:
             self.shape.append(len(self.ranges[p]))
 
     def filter_model(self, m, filtermethod='savitzkygolay', nbins=101, order=3, filterknee=(1. / (0.3 * 86400.))):
-        """model.py:94-131 (Savitzky-Golay only; the other filters belong to the legacy
-        ``Bayes.bayes_factors`` path, which is out of scope here)."""
-        from .noise import savitzky_golay
+        """model.py:94-131"""
+        from .noise import savitzky_golay, running_median, highpass_filter_lightcurve
         if filtermethod == 'savitzkygolay':
             return m - savitzky_golay(m, nbins, order)
+        if filtermethod == 'runningmedian':
+            return m - running_median(m, nbins)
+        if filtermethod == 'highpass':
+            from .lightcurve import Lightcurve
+            return highpass_filter_lightcurve(Lightcurve(cts=np.copy(self.ts), clc=np.copy(m)), knee=filterknee)
         raise ValueError('Unrecognised filter method (%s) given' % filtermethod)
 
     def _pdict(self, q):

@@ -10,7 +10,7 @@ from math import factorial
 
 import numpy as np
 
-__all__ = ["estimate_noise_ps", "estimate_noise_tv", "savitzky_golay", "nextpow2"]
+__all__ = ["running_median", "highpass_filter_lightcurve", "estimate_noise_ps", "estimate_noise_tv", "savitzky_golay", "nextpow2"]
 
 
 def nextpow2(i):
@@ -75,3 +75,32 @@ def estimate_noise_tv(d, sigma=1.0):
     highS = interpf(0.5 + cp / 2.)
     m = interpf(0.5)
     return (highS - lowS) / (2. * sigma), m
+
+
+def running_median(y, window):
+    """Running median with a window that shrinks at the edges (noise.py:291-317): sample ``i`` uses
+    the indices strictly between ``i - window/2`` and ``i + window/2``."""
+    y = np.asarray(y, dtype=float)
+    n = len(y)
+    halfwin = int(window / 2)
+    ffit = np.empty(n)
+    for i in range(n):
+        ffit[i] = np.median(y[max(0, i - halfwin + 1):min(n, i + halfwin)])
+    return ffit
+
+
+def highpass_filter_lightcurve(lightcurve, knee=(1. / (0.3 * 86400.))):
+    """Third-order Butterworth high-pass applied to the time-reversed series followed by the series itself,
+    keeping the second half (noise.py:254-288).  Returns the filtered array.  (The reference indexes with
+    ``np.floor(len(y)/2)``, a float, which modern NumPy rejects; the integer meant is used.)"""
+    from scipy import signal
+    z = np.asarray(lightcurve.clc, dtype=float)
+    dt = lightcurve.dt()
+    if dt <= 0:
+        raise NameError
+    highcut = knee / (1. / (2. * dt))
+    zd = np.concatenate((z[::-1], z))
+    b, a = signal.butter(3, highcut, btype='highpass')
+    y = signal.lfilter(b, a, zd)
+    return y[len(y) // 2:]
+

@@ -313,6 +313,8 @@ def gold_ingest(bf):
     tmp = copy.copy(lc)
     tmp.detrend(method='savitzkygolay', nbins=odds.bglen, order=odds.bgorder)
     out["ref_sk"] = np.array(bf.estimate_noise_tv(tmp.clc, sigma=odds.tvsigma)[0])
+    # the running-median detrender (noise.py:291-317) on the conditioned curve
+    out["ref_running_median_21"] = bf.running_median(out["ref_clc"], 21)
     save("ingest", **out)
     print("   ingest: %d segments, nan lnO %d, max %.3f" % (n, int(np.isnan(out["ref_lnO"]).sum()), np.nanmax(out["ref_lnO"])))
 

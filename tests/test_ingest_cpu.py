@@ -114,3 +114,20 @@ def test_result_dictionary_format_and_merge(tmp_path):
     write_result(m, path)
     back = json.load(open(path))
     assert back["Flaring star data"]["KPLR000000002"]["Max. indices"] == [4]
+
+
+def test_detrenders_vs_reference():
+    g = load_golden("ingest")
+    np.testing.assert_array_equal(bf.running_median(g["ref_clc"], 21), g["ref_running_median_21"])
+    lc = bf.Lightcurve(cts=g["ref_cts"], clc=g["ref_clc"])
+    lc.detrend(method="runningmedian", nbins=21)
+    np.testing.assert_array_equal(lc.clc, g["ref_clc"] - g["ref_running_median_21"])
+    assert lc.detrended and lc.detrend_method == "runningmedian"
+    hp = bf.Lightcurve(cts=g["ref_cts"], clc=g["ref_clc"])
+    hp.detrend(method="highpassfilter", knee=1. / (0.3 * 86400.))
+    assert len(hp.clc) == len(g["ref_clc"]) and np.all(np.isfinite(hp.clc))
+    assert np.std(hp.clc) < np.std(g["ref_clc"])               # the slow trend is gone
+    with pytest.raises(ValueError):
+        bf.Lightcurve(cts=g["ref_cts"], clc=g["ref_clc"]).detrend(method="runningmedian")
+    with pytest.raises(ValueError):
+        bf.Lightcurve(cts=g["ref_cts"], clc=g["ref_clc"]).detrend(method="nonsense", nbins=5)
