@@ -6,7 +6,7 @@
 // "template g + polynomial background" against Gaussian noise on a W-sample window
 // centred on k; then a trapezium log-sum-exp over g and the combination of hypotheses.
 //
-// Two paths, both fp64 on the vector pipe:
+// Three paths, all fp64 on the vector pipe:
 //
 //  * FAST path (interior samples, noise variance constant along the curve).  The Gram
 //    matrix of [polynomials | template] is translation invariant, so its factorisation is
@@ -19,12 +19,22 @@
 //    (log_marg_amp_full.c:29-66) but better conditioned (no Hilbert-like pivots).
 //    The thread keeps its KT+W-1 data window in registers; templates are broadcast from
 //    shared memory; the log-sum-exp over the grid is online, so per-grid values never
-//    reach HBM in detector mode.
+//    reach HBM in detector mode.  A flare grid is separable (rise + decay shapes), and large
+//    batches run the split form: k_corr_shapes (shape correlations) + k_epilogue (grid sum in the
+//    linear domain, hypotheses combined).
+//
+//  * WEIGHTED path (interior samples of curves with per-sample variance, i.e. real light curves
+//    with flux errors): the same integral with a per-sample P x P Cholesky in the orthonormal
+//    basis (k_window_wsep separable, k_window_weighted dense / full output).
 //
 //  * GENERAL path (first/last W/2 samples where the reference truncates the window,
-//    bayes.py:320-327, and curves with per-sample variance).  Every cross term is rebuilt
-//    per sample in the reference's own summation order (NumPy pairwise) and the
-//    elimination is replayed in the reference's order without FMA contraction.
+//    bayes.py:320-327).  These systems are ill conditioned and the reference's answer depends on
+//    its rounding: every cross term is rebuilt per sample in the reference's own summation order
+//    (NumPy pairwise) and the elimination is replayed in the reference's order without FMA
+//    contraction.
+//
+// Further down: plan kernels (templates, orthonormalisation), noise estimate (Savitzky-Golay,
+// periodogram, tail veto), parameter-estimation grid, thresholding, the injection sweep.
 #include "bfl_kernels.cuh"
 
 #include <math.h>
@@ -2265,7 +2275,7 @@ struct CombArgs {
   const double2* part;
   const double* bgabs;
   int64_t BK;          // B * nk
-  int nhyp, NC, gchunk, G, noisepoly, sub;   // sub: partials per template chunk (2 with the warp-specialised kernel)
+  int nhyp, NC, gchunk, G, noisepoly, sub;   // sub: partial-sum slots per template chunk (1 for every current kernel)
   int hyp_begin[MAXH + 1];
   double* lnO;
   double* marg;        // [(nhyp+1)][BK] or nullptr

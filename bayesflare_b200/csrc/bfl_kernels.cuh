@@ -81,7 +81,7 @@ struct Scratch {
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
-  int sub;         // partials per template chunk: 2 when the warp-specialised kernel runs, else 1
+  int sub;         // partial-sum slots per template chunk (1 for every current kernel)
 };
 
 struct LaunchStats { int64_t launches = 0; };
