@@ -138,3 +138,26 @@ def test_contiguous_regions_and_detector_config():
         det.set_flare_params({"tauexp": (1, 2, 3)})
     with pytest.raises(NotImplementedError):
         bf.OddsRatioDetector(lc, nsinusoids=2).plan()
+
+
+def test_impulse_excluder_m_shaped_features():
+    """find.py:866-912: a dip below -5 flanked by rising then falling positive pairs removes
+    [idx - width, idx + width) (clamped); anything else is kept"""
+    import bayesflare_b200 as bf
+    n = 60
+    lnO = np.full(n, -1.0)
+    ts = np.arange(n, dtype=float)
+    for c in (20, 3, 57):                       # interior M shape, one near each end (clamped windows)
+        lnO[c - 2:c + 3] = [1.0, 3.0, -8.0, 3.0, 1.0]
+    lnO[40] = -9.0                              # a dip without the flanks: kept
+    lnO[48:53] = [3.0, 1.0, -8.0, 3.0, 1.0]     # left flank falls instead of rising: kept
+    det = bf.OddsRatioDetector(bf.Lightcurve(cts=ts * 1765.5, clc=np.zeros(n)))
+    got, gts = det.impulse_excluder(lnO, ts, exclusionwidth=5)
+    keep = np.ones(n, dtype=bool)
+    keep[15:25] = False
+    keep[0:8] = False
+    keep[52:59] = False                         # enidx clamps to len - 1, the last sample survives
+    np.testing.assert_array_equal(gts, ts[keep])
+    np.testing.assert_array_equal(got, lnO[keep])
+    got2, _ = det.impulse_excluder(list(lnO), ts, exclusionwidth=2)
+    assert len(got2) == n - 4 - 4 - 4
