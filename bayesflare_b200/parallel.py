@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["shard_range", "time_chunks", "gather_detections", "allreduce_counts"]
+__all__ = ["gather_objects", "shard_range", "time_chunks", "gather_detections", "allreduce_counts"]
 
 
 def shard_range(n, world, rank):
@@ -81,3 +81,14 @@ def allreduce_counts(counts, device="cpu", group=None):
     t = torch.from_numpy(counts.copy()).to(device)
     dist.all_reduce(t, group=group)
     return t.cpu().numpy()
+
+
+def gather_objects(obj, group=None):
+    """All-gather one picklable object per rank (e.g. the result dictionary of a sharded search); returns the
+    list in rank order on every rank, or ``[obj]`` without a process group."""
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        return [obj]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out

@@ -166,3 +166,45 @@ def write_result(outdict, path):
         raise TypeError(type(o))
     with open(path, "w") as f:
         json.dump(outdict, f, indent=2, default=default)
+
+
+def main(argv=None):
+    """``python -m bayesflare_b200.search 'Q1_public/kplr*_llc.fits' --out flares.json``; under ``torchrun`` the
+    files are sharded over the ranks (one GPU each) and rank 0 merges and writes the result."""
+    import argparse
+    import glob
+    import os
+    from .parallel import gather_objects, shard_range
+    ap = argparse.ArgumentParser(description="Kepler flare search (scripts/kepler_analysis_script.py) on the GPU")
+    ap.add_argument("files", nargs="+", help="light-curve FITS files or glob patterns")
+    ap.add_argument("--threshold", type=float, default=16.5)
+    ap.add_argument("--expand", type=int, default=1)
+    ap.add_argument("--maxgap", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--out", default="flare_search.json")
+    args = ap.parse_args(argv)
+    files = sorted(f for pat in args.files for f in (glob.glob(pat) or [pat]))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lo, hi = shard_range(len(files), world, rank)
+    res = flare_search(files[lo:hi], threshold=args.threshold, expand=args.expand, maxgap=args.maxgap, batch=args.batch,
+                       device=local_rank if world > 1 else None)
+    allres = gather_objects(res)
+    if rank == 0:
+        merged = merge_results(allres)
+        write_result(merged, args.out)
+        print("%d stars analysed on %d GPU(s), %d flares in %d stars -> %s"
+              % (merged["No. stars analysed"], world, merged["No. flares"], len(merged["Flaring stars"]), args.out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

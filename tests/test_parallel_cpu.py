@@ -59,7 +59,16 @@ def _worker(rank, world, port, q):
         hist[rank::7] = rank + 1
         tot = parallel.allreduce_counts(hist)
         empty = parallel.gather_detections(np.zeros((0, 5)))
-        q.put((rank, allrec, tot, empty.shape))
+        # per-rank result dictionaries of a sharded flare search, merged as rank 0 would
+        from bayesflare_b200.search import merge_results, new_result
+        mine = new_result(16.5, nstars=hi - lo)
+        mine["Star list"] = list(range(lo, hi)); mine["No. stars analysed"] = hi - lo
+        mine["Flaring stars"] = [c for c in range(lo, hi) if c % 4 == 0]
+        mine["No. flares"] = len(mine["Flaring stars"])
+        for c in mine["Flaring stars"]:
+            mine["Flaring star data"]["KPLR%09d" % c] = {"Kepler ID": c, "No. flares": 1}
+        merged = merge_results(parallel.gather_objects(mine))
+        q.put((rank, allrec, tot, empty.shape, merged))
     finally:
         dist.destroy_process_group()
 
@@ -81,9 +90,13 @@ def test_gather_and_reduce_world2_gloo():
     hist = np.zeros(50, dtype=np.int64)
     hist[0::7] += 1
     hist[1::7] += 2
-    for rank, allrec, tot, eshape in res:
+    for rank, allrec, tot, eshape, merged in res:
         np.testing.assert_array_equal(allrec, expect)      # identical on every rank, rank order preserved
         np.testing.assert_array_equal(tot, hist)
+        assert merged["Star list"] == list(range(10)) and merged["No. stars analysed"] == 10
+        assert merged["Flaring stars"] == [0, 4, 8] and merged["No. flares"] == 3
+        assert sorted(merged["Flaring star data"]) == ["KPLR000000000", "KPLR000000004", "KPLR000000008"]
+        assert merged["Total no. of stars"] == 10
         assert eshape == (0, 5)
 
 
