@@ -167,6 +167,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")           # no NCCL version banner in front of the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm_device = "cuda:%d" % local_rank
     t0 = time.perf_counter()

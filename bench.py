@@ -177,8 +177,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")           # both levels print NCCL's version banner on stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     B, N = args.curves, args.samples
     NB = 8                                        # rotating input batches: 8 x 36 MB > 126 MB L2
