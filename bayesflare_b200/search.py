@@ -73,13 +73,21 @@ def _star_record(kepid, info, lnO, ts, flarelist, nflares, maxlist, sk, dc):
 
 
 def flare_search(curves, threshold=16.5, expand=1, maxgap=2, batch=256, star_info=None, outdict=None,
-                 detector_kwargs=None, device=None):
+                 detector_kwargs=None, device=None, checkpoint=None):
     """Search light curves for flares.
 
     ``curves``: file names of Kepler light-curve FITS files and/or :class:`Lightcurve` objects.
     ``star_info``: optional ``{kepid: {"teff": .., "logg": ..}}``.  ``outdict``: a result dictionary to
     continue (stars already in its ``"Star list"`` are skipped, as the script does on restart).
-    Returns the result dictionary (see :func:`new_result`)."""
+    ``checkpoint``: a file name; the dictionary is written there after every batch (the script rewrites its
+    output file as it goes, ``:343-351``) and, if the file exists and ``outdict`` is not given, the search
+    resumes from it.  Returns the result dictionary (see :func:`new_result`)."""
+    if checkpoint is not None and outdict is None:
+        try:
+            with open(checkpoint) as f:
+                outdict = json.load(f)
+        except (OSError, ValueError):
+            outdict = None
     star_info = star_info or {}
     out = outdict if outdict is not None else new_result(threshold, nstars=len(curves))
     done = set(out["Star list"])
@@ -135,6 +143,8 @@ def flare_search(curves, threshold=16.5, expand=1, maxgap=2, batch=256, star_inf
                     out["Flaring stars"].append(lc.id)
                     out["Flaring star data"]["KPLR%09d" % int(lc.id)] = _star_record(
                         lc.id, star_info.get(lc.id, {}), lnO[i], ts, flarelist, nfl, maxlist, sks[i], lc.dc)
+            if checkpoint is not None:
+                write_result(out, checkpoint)
     return out
 
 
@@ -182,6 +192,7 @@ def main(argv=None):
     ap.add_argument("--maxgap", type=int, default=2)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--out", default="flare_search.json")
+    ap.add_argument("--checkpoint", default=None, help="per-rank checkpoint file prefix: written after every batch, resumed from")
     args = ap.parse_args(argv)
     files = sorted(f for pat in args.files for f in (glob.glob(pat) or [pat]))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,7 +205,8 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lo, hi = shard_range(len(files), world, rank)
     res = flare_search(files[lo:hi], threshold=args.threshold, expand=args.expand, maxgap=args.maxgap, batch=args.batch,
-                       device=local_rank if world > 1 else None)
+                       device=local_rank if world > 1 else None,
+                       checkpoint=("%s.rank%d.json" % (args.checkpoint, rank)) if args.checkpoint else None)
     allres = gather_objects(res)
     if rank == 0:
         merged = merge_results(allres)

@@ -3,6 +3,8 @@ against (a) golden fixtures generated from the reference and (b) the CPU oracle 
 
 Tolerance (BASELINE.json north_star): |delta| <= 1e-9 * max(1, |ref|) on log odds / log Bayes
 factors with an identical -inf pattern; detection indices bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -553,6 +555,13 @@ def test_kepler_search_from_fits_files_vs_reference(tmp_path):
     # restart: already analysed stars are skipped
     again = bf.flare_search(paths, threshold=16.5, outdict=out)
     assert again["No. stars analysed"] == 3
+    # checkpoint file: written after every batch, resumed from when present
+    ck = str(tmp_path / "ck.json")
+    first = bf.flare_search(paths[:2], threshold=16.5, checkpoint=ck, batch=1)
+    assert first["No. stars analysed"] == 2 and os.path.exists(ck)
+    resumed = bf.flare_search(paths, threshold=16.5, checkpoint=ck)
+    assert resumed["Star list"] == [1001, 1002, 1003] and resumed["No. flares"] == out["No. flares"]
+    assert resumed["Flaring star data"].keys() == out["Flaring star data"].keys()
 
 
 @pytest.mark.gpu
