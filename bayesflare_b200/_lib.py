@@ -92,7 +92,7 @@ SIGNATURES = {
     "bfl_threshold": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_double, C.c_int32, _i64p, _dp, _i64p, C.c_int32,
                                 C.POINTER(C.c_int32)]),
     "bfl_pe_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, C.c_int64, C.c_int32,
-                              _dp, C.c_double, C.c_int32, _dp]),
+                              _dp, C.c_double, C.c_int32, _dp, C.c_int32, _dp]),
     "bfl_logtrapz": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64, _dp]),
     "bfl_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
 }
@@ -342,14 +342,19 @@ def threshold(ctx, lnO, thresh, expand=0):
     return segs[:k], mv[:k], mi[:k]
 
 
-def pe_grid(ctx, kind, reverse, cts, clc, params, logprior, npoly, polyms, sigma, margbackground):
+def pe_grid(ctx, kind, reverse, cts, clc, params, logprior, npoly, polyms, sigma, margbackground, sg=None):
+    """``sg = (nbins, order)``: the chunk was Savitzky-Golay detrended, filter every model the same way."""
     cts, clc, params, logprior = f64(cts), f64(clc), f64(params), f64(logprior)
     G = logprior.size
     polyms = None if polyms is None else f64(polyms)
     out = np.empty(G)
+    coef = None
+    if sg is not None:
+        from .noise import _sg_coefficients
+        coef = f64(_sg_coefficients(int(sg[0]), int(sg[1])))
     check(ctx.lib.bfl_pe_grid(ctx.handle, MODEL_KINDS[kind], 1 if reverse else 0, ptr(cts), ptr(clc), cts.size,
                               ptr(params), ptr(logprior), G, int(npoly), ptr(polyms), float(sigma),
-                              1 if margbackground else 0, ptr(out)))
+                              1 if margbackground else 0, ptr(coef), 0 if coef is None else coef.size, ptr(out)))
     return out
 
 

@@ -300,9 +300,10 @@ class ParameterEstimationGrid:
         else:
             pv = self.paramValues
         lc = lightcurve if lightcurve is not None else self.lightcurve
+        # a Savitzky-Golay detrended chunk: every model is filtered the same way (bayes.py:1018-1021)
+        sg = None
         if getattr(lc, "detrended", False) and getattr(lc, "detrend_method", None) == 'savitzkygolay':
-            raise NotImplementedError("posterior on a Savitzky-Golay detrended chunk (bayes.py:1019-1021) "
-                                      "is not covered by the GPU path")
+            sg = (getattr(lc, "detrend_nbins", None) or lc.detrend_length, lc.detrend_order)
         # NOTE (as the reference, bayes.py:1039 and :1046): the likelihood always uses
         # self.noiseSigma, even when ``sigma`` is passed.
         sk = self.noiseSigma
@@ -322,7 +323,7 @@ class ParameterEstimationGrid:
             ts01 = np.linspace(0, 1, dl)
             polyms = np.array([ts01 ** i for i in range(bgorder + 1)])
         post = _lib.pe_grid(_lib.default_context(), self.model.device_kind, self.model.reverse, lc.cts, lc.clc,
-                            params, logprior, bgorder + 1, polyms, sk, margbackground)
+                            params, logprior, bgorder + 1, polyms, sk, margbackground, sg=sg)
         self.posterior = post.reshape(tuple(sp))
 
     # ---- post-processing (host; bayes.py:1057-1301) ---------------------------------------

@@ -931,8 +931,10 @@ int bfl_threshold(bfl_ctx* c, const double* lnO, int64_t n, double thresh, int32
 // --------------------------------------------------------------------------------------
 int bfl_pe_grid(bfl_ctx* c, int32_t kind, int32_t reverse, const double* cts, const double* clc, int64_t L,
                 const double* params, const double* logprior, int64_t G, int32_t P, const double* polyms,
-                double sigma, int32_t margbackground, double* out_post) {
+                double sigma, int32_t margbackground, const double* sgcoef, int32_t sgbins, double* out_post) {
   if (!c || !cts || !clc || !params || !logprior || !out_post) return fail(BFL_ERR_ARG, "null argument to bfl_pe_grid");
+  if (sgcoef && (sgbins < 3 || sgbins % 2 == 0 || sgbins > MAXW || (sgbins - 1) / 2 + 1 > L))
+    return fail(BFL_ERR_ARG, "window_size size must be a positive odd number");
   if (margbackground && !polyms) return fail(BFL_ERR_ARG, "polyms required when margbackground is set");
   if (kind < 0 || kind >= BFL_MODEL_TABLE) return fail(BFL_ERR_ARG, "bad model kind");
   if (L < 2 || L > 200) return fail(BFL_ERR_UNSUPPORTED, "chunk length must be in 2..200 samples");
@@ -954,9 +956,14 @@ int bfl_pe_grid(bfl_ctx* c, int32_t kind, int32_t reverse, const double* cts, co
   CK(cudaMemcpyAsync(d_par, params, sizeof(double) * 4 * (size_t)G, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(d_lp, logprior, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, s));
   if (margbackground) CK(cudaMemcpyAsync(d_poly, polyms, sizeof(double) * (size_t)P * L, cudaMemcpyHostToDevice, s));
+  void* d_sg = nullptr;
+  if (sgcoef) {
+    if ((rc = c->get("pe_sg", sizeof(double) * MAXW, &d_sg))) return rc;
+    CK(cudaMemcpyAsync(d_sg, sgcoef, sizeof(double) * (size_t)sgbins, cudaMemcpyHostToDevice, s));
+  }
   CK(launch_pe_grid(kind, reverse, (const double*)d_cts, (const double*)d_clc, (int)L, (const double*)d_par,
-                    (const double*)d_lp, G, P, (const double*)d_poly, sigma, margbackground, (double*)d_post, s,
-                    &c->stats));
+                    (const double*)d_lp, G, P, (const double*)d_poly, sigma, margbackground, (double*)d_post,
+                    (const double*)d_sg, sgbins, s, &c->stats));
   CK(cudaMemcpyAsync(out_post, d_post, sizeof(double) * (size_t)G, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return BFL_OK;

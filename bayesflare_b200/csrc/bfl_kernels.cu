@@ -2465,7 +2465,10 @@ struct PeArgs {
   int64_t G;
   double sigma;
   double* post;
+  const double* sgcoef; // Savitzky-Golay taps when the chunk was detrended (bayes.py:1018-1021), else nullptr
+  int sgbins;
 };
+constexpr int PE_MAXL = 200;
 
 // background-only sums shared by every grid point (bayes.py:981-1000), NumPy order
 __global__ void k_pe_setup(const double* __restrict__ clc, const double* __restrict__ polyms, int L, int P,
@@ -2505,6 +2508,26 @@ __global__ void __launch_bounds__(128) k_pe_grid(const PeArgs a) {
   for (int i = 0; i < 4; i++) p[i] = a.params[g * 4 + i];
   const double t0c = sts[L / 2];
   for (int i = 0; i < L; i++) sm[i * 128 + tid] = model_value(a.kind, a.reverse, p, sts[i], t0c, sts[0], sts, L);
+  if (a.sgbins > 0) {
+    // the light curve was Savitzky-Golay detrended: the model gets the same treatment, m - savitzky_golay(m)
+    // (noise.py:176-252: mirrored-difference padding, then the FIR; same arithmetic as k_sg_resid)
+    double filt[PE_MAXL];
+    const int W = a.sgbins, h = (W - 1) / 2;
+    const double y0 = sm[tid], yl = sm[(L - 1) * 128 + tid];
+    for (int i = 0; i < L; i++) {
+      double fit = 0.0;
+      for (int j = 0; j < W; j++) {
+        const int t = i + j;
+        double v;
+        if (t < h) v = y0 - fabs(sm[(h - t) * 128 + tid] - y0);
+        else if (t < h + L) v = sm[(t - h) * 128 + tid];
+        else v = yl + fabs(sm[(L - 2 - (t - h - L)) * 128 + tid] - yl);
+        fit = fma(a.sgcoef[j], v, fit);
+      }
+      filt[i] = sm[i * 128 + tid] - fit;
+    }
+    for (int i = 0; i < L; i++) sm[i * 128 + tid] = filt[i];
+  }
   double res;
   if (a.margbackground) {
     double Mu[NM][NM], D[NM];
@@ -2536,8 +2559,9 @@ __global__ void __launch_bounds__(128) k_pe_grid(const PeArgs a) {
 cudaError_t launch_pe_grid(int kind, int reverse, const double* d_cts, const double* d_clc, int L,
                            const double* d_params, const double* d_logprior, int64_t G, int P,
                            const double* d_polyms, double sigma, int margbackground, double* d_post,
-                           cudaStream_t s, LaunchStats* st) {
+                           const double* d_sgcoef, int sgbins, cudaStream_t s, LaunchStats* st) {
   PeArgs a;
+  a.sgcoef = d_sgcoef; a.sgbins = d_sgcoef ? sgbins : 0;
   a.kind = kind; a.reverse = reverse; a.L = L; a.margbackground = margbackground;
   a.cts = d_cts; a.clc = d_clc; a.params = d_params; a.logprior = d_logprior; a.polyms = d_polyms;
   a.G = G; a.sigma = sigma; a.post = d_post;

@@ -128,7 +128,7 @@ cudaError_t launch_combine(const PlanView& pv, const SeriesView& sv, const Scrat
 cudaError_t launch_pe_grid(int kind, int reverse, const double* d_cts, const double* d_clc, int L,
                            const double* d_params, const double* d_logprior, int64_t G, int P,
                            const double* d_polyms, double sigma, int margbackground, double* d_post,
-                           cudaStream_t s, LaunchStats* st);
+                           const double* d_sgcoef, int sgbins, cudaStream_t s, LaunchStats* st);
 
 cudaError_t launch_logtrapz(const double* d_lx, const double* d_t, int64_t n, int64_t m, double* d_out,
                             cudaStream_t s, LaunchStats* st);

@@ -198,10 +198,13 @@ int bfl_threshold(bfl_ctx* ctx, const double* lnO, int64_t n, double thresh, int
  * log_likelihood_ratio (general.pyx:659-691) otherwise.  One light-curve chunk:
  *   cts, clc host [L]; grid: kind + params host [G][4] (+ logprior host [G]); P = bgorder+1
  *   polyms host [P][L]: linspace(0,1,L)**p as the caller's NumPy computed it (bayes.py:984-988)
+ *   sgcoef host [sgbins] or NULL: when the chunk was Savitzky-Golay detrended, the filter taps (the same
+ *   array bfl_noise_spec.sgcoef takes); every model gets m - savitzky_golay(m) as bayes.py:1018-1021 does
  *   out_post host [G] = log likelihood + log prior                                      */
 int bfl_pe_grid(bfl_ctx* ctx, int32_t kind, int32_t reverse, const double* cts, const double* clc,
                 int64_t L, const double* params, const double* logprior, int64_t G, int32_t P,
-                const double* polyms, double sigma, int32_t margbackground, double* out_post);
+                const double* polyms, double sigma, int32_t margbackground, const double* sgcoef, int32_t sgbins,
+                double* out_post);
 
 /* ---- logtrapz (general.pyx:576-607) over the leading axis of lx[n][m] -> out[m] ------ */
 int bfl_logtrapz(bfl_ctx* ctx, const double* lx, const double* t, int64_t n, int64_t m, double* out);

@@ -274,6 +274,17 @@ def gold_pe(bf):
     pe.set_grid(ranges={"taugauss": (0., 3600., 6), "tauexp": (0., 12000., 5), "amp": amprange, "t0": (t0,)})
     pe.calculate_posterior(margbackground=False)
     out["ref_post_nobg"] = pe.posterior
+    # a Savitzky-Golay detrended chunk: the reference filters every model the same way (bayes.py:1018-1021).
+    # (set_detrend stores the window as detrend_length but calculate_posterior reads detrend_nbins, which
+    # stays 0 -- data.py:373 vs bayes.py:1020 -- so the window is set by hand here, as a user would have to.)
+    pe = bf.ParameterEstimationGrid("flare", lc)
+    pe.lightcurve_chunk(idxt0, 55)
+    pe.lightcurve.detrend(method="savitzkygolay", nbins=21, order=3)
+    pe.lightcurve.detrend_nbins = 21
+    pe.set_grid(ranges={"taugauss": (0., 3600., 6), "tauexp": (0., 12000., 5), "amp": amprange, "t0": (t0,)})
+    pe.calculate_posterior(bgorder=2)
+    out["ref_post_sg21_o2"] = pe.posterior
+    out["ref_sg_chunk_clc"] = pe.lightcurve.clc.copy()
     save("pegrid", **out)
 
 

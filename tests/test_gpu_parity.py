@@ -291,6 +291,14 @@ def test_parameter_estimation_grid_vs_reference():
     pe.set_grid(ranges={'taugauss': (0., 3600., 6), 'tauexp': (0., 12000., 5), 'amp': (a[0], a[1], int(a[2])), 't0': (t0,)})
     pe.calculate_posterior(margbackground=False)
     assert_logodds_close(pe.posterior, g["ref_post_nobg"], TOL, "pe no background")
+    # Savitzky-Golay detrended chunk: every model is filtered the same way (bayes.py:1018-1021)
+    pe = bf.ParameterEstimationGrid('flare', lc)
+    pe.lightcurve_chunk(idx, 55)
+    pe.lightcurve.detrend(method="savitzkygolay", nbins=21, order=3)
+    np.testing.assert_allclose(pe.lightcurve.clc, g["ref_sg_chunk_clc"], rtol=0, atol=1e-12)
+    pe.set_grid(ranges={'taugauss': (0., 3600., 6), 'tauexp': (0., 12000., 5), 'amp': (a[0], a[1], int(a[2])), 't0': (t0,)})
+    pe.calculate_posterior(bgorder=2)
+    assert_logodds_close(pe.posterior, g["ref_post_sg21_o2"], TOL, "pe on a detrended chunk")
 
 
 def test_dense_grid_property_and_oracle_subset():
