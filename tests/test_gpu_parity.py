@@ -731,3 +731,25 @@ def test_sweep_on_device_simulation_scoring_and_statistics():
     mid_d = whole["detected"][5:15].sum() / whole["injected"][5:15].sum()
     mid_h = host["detected"][5:15].sum() / host["injected"][5:15].sum()
     assert abs(mid_d - mid_h) < 0.08                         # transition region: binomial scatter of ~600 curves
+
+
+@pytest.mark.gpu
+def test_long_series_time_chunks_driver():
+    """`longseries.oddsratio_time_chunks`: the pieces 4 ranks would compute, concatenated, are the whole
+    series (bit for bit: a chunk only changes which samples a launch covers)"""
+    from bayesflare_b200.longseries import oddsratio_time_chunks
+    rng = np.random.default_rng(3)
+    N = 30000
+    cts = np.arange(N) * 58.84876
+    x = rng.standard_normal(N)
+    x[12000:12400] += 9.0 * np.exp(-np.arange(400) * 58.84876 / 900.)
+    det = bf.OddsRatioDetector(_lc(cts, x))
+    whole, _ = oddsratio_time_chunks(det, x, sk=1.0, rank=0, world=1)
+    lnO, _ = det.oddsratio()
+    assert len(whole) == N - 54
+    pieces = [oddsratio_time_chunks(det, x, sk=1.0, rank=r, world=4, gather=False)[0] for r in range(4)]
+    np.testing.assert_array_equal(np.concatenate(pieces), whole)
+    assert np.argmax(whole) in range(12000 - 27 - 3, 12000 - 27 + 4) and whole.max() > 16.5
+    sk = float(det.noise_sigma_batch(x)[0])
+    auto, _ = oddsratio_time_chunks(det, x, rank=0, world=1)          # sigma estimated on the device
+    np.testing.assert_allclose(auto, np.array(lnO), rtol=1e-10, atol=1e-10)
