@@ -502,7 +502,7 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   if ((rc = c->get("sqrtu", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.sqrtu = (double*)ptr;
   if ((rc = c->get("halflogv", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.halflogv = (double*)ptr;
   if ((rc = c->get("uconst", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.uconst = (double*)ptr;
-  if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)sc.NC, &ptr))) return rc;
+  if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)(sc.NC + 1), &ptr))) return rc;
   sc.tile_counters = (unsigned long long*)ptr;
   sc.dw = sc.uu = nullptr;
   if (need_general) {

@@ -384,8 +384,8 @@ __global__ void k_prep_whiten(const double* __restrict__ clc, const double* __re
 }
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st) {
-  k_prep_scalars<<<(std::max(sv.B, sc.NC) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
-                                                                   sc.uconst, sc.tile_counters, sc.NC);
+  k_prep_scalars<<<(std::max(sv.B, sc.NC + 1) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
+                                                                   sc.uconst, sc.tile_counters, sc.NC + 1);
   st->launches++;
   if (need_general) {
     const int64_t n = sv.seglen * sv.B;
@@ -788,6 +788,9 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_corr_shapes(const CorrArgs a) {
 struct EpiArgs {
   const double* Y;        // [S][BK]
   const double* halflogv; // [B]
+  const double* sqrtu;    // [B]
+  unsigned long long* tile_counter;   // k_epilogue2: next warp tile (zeroed by k_prep_scalars)
+  int srows;              // k_epilogue2: rows of the per-thread slice (A shapes of separable + all shapes of dense hypotheses)
   int64_t nk, BK, N, k0;
   int B, G, nhyp, H;
   int hyp_begin[MAXH + 1];
@@ -1020,6 +1023,395 @@ __global__ void __launch_bounds__(EPI_TPB, BFL_EPI_MINB) k_epilogue(const EpiArg
   }
 }
 
+// --------------------------------------------------------------------------------------
+// k_epilogue2: the same stage with the E(z) evaluation in mixed precision (tools/gen_exphi2_table.py).
+// ncu of k_epilogue (round 1): 56 warp instructions per (32 samples, template), 28 of them FP64, two
+// F2I/I2F on the XU pipe, FP64 pipe 49 % busy.  Only the part of E(z) that needs 53 bits stays in fp64
+// (10 instructions): E_k (1 + t + t^2/2) with t = (z - z_k) phi'(z_k).  The remainder of the series
+// (< 1e-5 of E) is evaluated in fp32 for the thread's two samples at once with the packed fp32x2
+// instructions of sm_100 (FFMA2 / FMUL2 / FADD2) and accumulated in a float per sample; fp32 copies
+// of the table row are made by integer truncation (two ALU instructions each), of z - z_k by one F2F.
+// A table row is (E_k, phi'(z_k)): still ONE 16-byte lane-varying load per evaluation.
+#include "exphi2_table.inc"
+struct __align__(16) EpiTC {   // per-template constants, one 32-byte broadcast record
+  double inorm;   // 1/|m_perp|
+  double c;       // exp(K_g + lp_g + lw_g - Cref_h)
+  float cf;       // (float)c
+  int aoff;       // offset of the template's A-shape row in the thread slice (idxA * SPT * EPI_TPB)
+  int pad0, pad1;
+};
+
+// shared-memory loads by 32-bit shared address (the table and the per-template records never change
+// after the kernel's prologue, so the loads need not be volatile)
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_b32x4(unsigned addr) {
+  int4 v;
+  asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int2 lds_b32x2(unsigned addr) {
+  int2 v;
+  asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64c(unsigned addr) {   // read-only data (the E table)
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void cp_async_f64(unsigned saddr, const double* gaddr) {   // LDGSTS: global -> shared, 8 bytes
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" : : "r"(saddr), "l"(gaddr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" : : : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" : : : "memory"); }
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" : : "r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {   // volatile: the A-shape slice is rewritten per hypothesis
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// positive normal float -> double, exact: three integer instructions
+__device__ __forceinline__ double f32pos_to_f64(float x) {
+  const unsigned b = (unsigned)__float_as_int(x);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+// positive, normal, float-range double -> float by truncation: two integer instructions
+__device__ __forceinline__ float f64pos_to_f32_trunc(double x) {
+  return __int_as_float(__funnelshift_l(__double2loint(x), __double2hiint(x) - 0x38000000, 3));
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {   // one MUFU.RCP, no denormal slow path
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ double rcp64_approx(double x) {   // one MUFU.RCP64H: ~20 good bits
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+// E(z) = E_k exp(t),  t = phi(z) - phi(z_k) to third order in d = z - z_k (|d| <= 1/256), e^t to fifth order.
+// One 8-byte look-up; 26 FP64 instructions.
+__device__ __forceinline__ double exphi2_one(double z6, unsigned tab, unsigned& kmax) {
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the low word of x + MAGIC is rint(x)
+  const double s = fma(z6, BFL_EXPHI2_INVH, MAGIC);
+  const unsigned k = (unsigned)__double2loint(s);
+  kmax = max(kmax, k);
+  const double Ek = lds_f64c(tab + 8u * min(k, (unsigned)(BFL_EXPHI2_NI - 1)));
+  const double kf = s - MAGIC;
+  const double d = fma(kf, -1.0 / BFL_EXPHI2_INVH, z6);
+  const double r0 = rcp64_approx(Ek);
+  const double r = fma(r0, fma(-Ek, r0, 1.0), r0);                    // 1 / E_k
+  const double g = r * 0.79788456080286535588;                         // sqrt(2/pi) / E_k
+  const double p1 = fma(kf, 1.0 / BFL_EXPHI2_INVH, -BFL_EXPHI2_ZC) + g; // first derivative of phi at z_k
+  const double p2 = fma(-g, p1, 1.0);                                  // second
+  const double p3 = g * fma(p1, p1, -p2);                              // third
+  const double t = d * fma(d, fma(d, p3 * (1.0 / 6.0), 0.5 * p2), p1);
+  double e = fma(t, 1.0 / 120.0, 1.0 / 24.0);
+  e = fma(e, t, 1.0 / 6.0);
+  e = fma(e, t, 0.5);
+  e = fma(e, t, 1.0);
+  e = fma(e, t, 1.0);
+  return Ek * e;
+}
+__device__ __forceinline__ void exphi2_pair(double z6a, double z6b, unsigned tab, double c0, double c1, double& S,
+                                            unsigned& kmax) {
+  const double ea = exphi2_one(z6a, tab, kmax), eb = exphi2_one(z6b, tab, kmax);
+  S = fma(c0, ea, S);
+  S = fma(c1, eb, S);
+}
+
+// two templates evaluated together: a pair inside the run of templates that share one B shape (separable
+// hypothesis), or two consecutive templates of a dense hypothesis.  An odd one out is paired with a copy of
+// itself of weight zero.
+struct __align__(16) EpiTP {
+  double inorm0, inorm1;
+  double c0, c1;
+  float cf0, cf1;
+  int aoff0, aoff1;       // byte offsets of the templates' A-shape rows in the thread slice
+};
+
+constexpr int EPI2_TPB = 256;   // one sample per thread: 64 registers, four CTAs (32 warps) per SM
+#ifndef BFL_EPI2_MINB
+#define BFL_EPI2_MINB 4
+#endif
+
+__device__ __forceinline__ long long f64_order_key(double x) {   // monotone map double -> signed 64-bit
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double f64_from_order_key(long long k) {
+  return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
+}
+
+// Log odds of one sample per thread from the shape correlations Y (fused detector mode only).
+//
+// LINEAR pass (every thread): nearly every sample is noise, where all |z| are a few units, so the grid sums are
+// accumulated as plain numbers.  The per-template weights carry every per-plan constant, including the
+// hypothesis' own normalisation, so all noise hypotheses add into ONE denominator sum and no exp / log-sum-exp
+// fold is needed between hypotheses:
+//     num = sum_{g in signal}  exp(K_g - M0)                    E(z_g)
+//     den = sum_{g in noise h} exp(K_g + hc_h [+ ZC^2/2] - M)   E_h(z_g)      (+ exp(-M) / sqrt(v) for the polynomial-only model)
+//     lnO = (M0 + hc_0 - M) + log(num / den)
+// with E_h = exp(phi) for half-range amplitudes (exphi2_pair) and exp(z^2/2 - ZC^2/2) for full-range ones.
+// LOG pass (only threads that met |z| > ZC, i.e. a flare or a deep dip): phi table + online log-sum-exp per
+// hypothesis, any z, as k_epilogue does.
+__global__ void __launch_bounds__(EPI2_TPB, BFL_EPI2_MINB) k_epilogue2(const EpiArgs a) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int G = a.G;
+  const int npairs_max = G / 2 + a.S + 1;
+  double* sT = smem;                                                   // [NI + 1] E_k
+  EpiTP* sTP = reinterpret_cast<EpiTP*>(sT + BFL_EXPHI2_NI + 1);       // [npairs_max]
+  EpiTC* sTC = reinterpret_cast<EpiTC*>(sTP + npairs_max);             // [G]  (full-range and log-domain loops)
+  double* sK = reinterpret_cast<double*>(sTC + G);                     // [G] Kg + lp + lw
+  double* sCref = sK + ((G + 1) & ~1);                                 // [MAXH] per-hypothesis maximum of sK (log pass)
+  double* sConst = sCref + MAXH;                                       // [2] lnO offset, weight of the polynomial-only model
+  long long* sKey = reinterpret_cast<long long*>(sConst + 2);          // [MAXH + 2] maxima under construction
+  double* ysm = reinterpret_cast<double*>(sKey + MAXH + 2);            // [srows][EPI2_TPB]
+  int* sG01 = reinterpret_cast<int*>(ysm + (size_t)a.srows * EPI2_TPB);   // [S][2] run of templates per B shape
+  int2* sRun = reinterpret_cast<int2*>(sG01 + 2 * a.S);                // [S] (byte offset of the run's first pair, pairs)
+  int* sRow = reinterpret_cast<int*>(sRun + a.S);                      // [S] row of shape s in the thread slice, or -1
+  constexpr double ZC = BFL_EXPHI2_ZC;
+  for (int i = tid; i < G; i += EPI2_TPB) sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
+  for (int i = tid; i < a.S; i += EPI2_TPB) { sG01[2 * i] = a.sh_g0[i]; sG01[2 * i + 1] = a.sh_g1[i]; }
+  for (int i = tid; i < BFL_EXPHI2_NI; i += EPI2_TPB) sT[i] = BFL_EXPHI2_TAB[i];
+  if (tid < MAXH + 2) sKey[tid] = (tid == MAXH && a.noisepoly) ? f64_order_key(0.0) : f64_order_key(-1.0e300);
+  __syncthreads();
+  for (int i = tid; i < G; i += EPI2_TPB) {
+    int h = 0;
+    while (a.hyp_begin[h + 1] <= i) h++;
+    atomicMax(sKey + h, f64_order_key(sK[i]));
+    if (h > 0) {
+      const double hc = a.hyp_half[h] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI) + 0.5 * ZC * ZC;
+      atomicMax(sKey + MAXH, f64_order_key(sK[i] + hc));
+    }
+  }
+  if (tid == 64) {   // rows of the thread slice: A shapes of separable hypotheses, every shape of dense ones
+    int row = 0;
+    for (int sidx = 0; sidx < a.S; sidx++) sRow[sidx] = -1;
+    for (int h = 0; h < a.nhyp; h++) {
+      if (a.hyp_nA[h] > 0) for (int ia = 0; ia < a.hyp_nA[h]; ia++) sRow[a.hyp_A0[h] + ia] = row++;
+      else for (int ib = 0; ib < a.hyp_nB[h]; ib++) sRow[a.hyp_B0[h] + ib] = row++;
+    }
+  }
+  if (tid == 32) {   // pair numbering: runs of a separable hypothesis one after the other, a dense hypothesis as one run
+    int cnt = 0;
+    for (int h = 0; h < a.nhyp; h++) {
+      if (a.hyp_nA[h] > 0) {
+        for (int sidx = a.hyp_B0[h]; sidx < a.hyp_B0[h] + a.hyp_nB[h]; sidx++) {
+          const int np = (sG01[2 * sidx + 1] - sG01[2 * sidx] + 1) / 2;
+          sRun[sidx] = make_int2(48 * cnt, np);
+          cnt += np;
+        }
+      } else {
+        const int np = (a.hyp_nB[h] + 1) / 2;
+        for (int sidx = a.hyp_B0[h]; sidx < a.hyp_B0[h] + a.hyp_nB[h]; sidx++) sRun[sidx] = make_int2(48 * cnt, np);
+        cnt += np;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < a.nhyp) sCref[tid] = f64_from_order_key(sKey[tid]);
+  if (tid == 0) {
+    const double M0 = f64_from_order_key(sKey[0]), M = f64_from_order_key(sKey[MAXH]);
+    const double hc0 = a.hyp_half[0] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI) + 0.5 * ZC * ZC;
+    sConst[0] = (M0 + hc0) - M;
+    sConst[1] = a.noisepoly ? exp(-M) : 0.0;
+  }
+  for (int i = tid; i < G; i += EPI2_TPB) {
+    int h = 0;
+    while (a.hyp_begin[h + 1] <= i) h++;
+    const double hc = a.hyp_half[h] ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI) + 0.5 * ZC * ZC;
+    const double Mh = (h == 0) ? f64_from_order_key(sKey[0]) : f64_from_order_key(sKey[MAXH]) - hc;
+    auto weight = [&](int g) { return exp(sK[g] - Mh); };
+    EpiTC tc;
+    tc.inorm = a.inorm[i];
+    tc.c = weight(i);
+    tc.cf = (float)tc.c;
+    tc.aoff = (int)a.idxA[i] * EPI2_TPB;
+    tc.pad0 = tc.pad1 = 0;
+    sTC[i] = tc;
+    // the pair record this template opens (even position in its run)
+    const int sB = a.idxB[i];
+    const int run0 = (a.hyp_nA[h] > 0) ? sG01[2 * sB] : a.hyp_begin[h];
+    const int run1 = (a.hyp_nA[h] > 0) ? sG01[2 * sB + 1] : a.hyp_begin[h + 1];
+    const int loc = i - run0;
+    if ((loc & 1) == 0) {
+      EpiTP tp;
+      const bool has2 = i + 1 < run1;
+      const int i2 = has2 ? i + 1 : i;
+      const double c2 = has2 ? weight(i2) : 0.0;
+      tp.inorm0 = tc.inorm; tp.inorm1 = a.inorm[i2];
+      tp.c0 = tc.c; tp.c1 = c2;
+      tp.cf0 = tc.cf; tp.cf1 = (float)c2;
+      tp.aoff0 = 8 * tc.aoff; tp.aoff1 = 8 * (int)a.idxA[i2] * EPI2_TPB;
+      sTP[sRun[sB].x / 48 + loc / 2] = tp;
+    }
+  }
+  __syncthreads();
+  const unsigned aT = (unsigned)__cvta_generic_to_shared(sT);
+  const unsigned aTP = (unsigned)__cvta_generic_to_shared(sTP);
+  const unsigned aRun = (unsigned)__cvta_generic_to_shared(sRun);
+  const unsigned aY = (unsigned)__cvta_generic_to_shared(ysm + tid);
+  const double lnO_off = sConst[0], w_poly = sConst[1];
+
+  // dynamic scheduling per WARP: a warp tile is 32 consecutive samples; warps never wait for each other
+  // (a tile with a flare costs three times a noise tile, so a static split leaves SMs idle at the end)
+  const int lane = tid & 31;
+  const int64_t nwt = (a.BK + 31) / 32;
+  for (;;) {
+    long long wt = 0;
+    if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
+    wt = __shfl_sync(0xffffffffu, wt, 0);
+    if (wt >= nwt) break;
+    int64_t idx = wt * 32 + lane;
+    bool valid = idx < a.BK;
+    if (!valid) idx = a.BK - 1;
+    const int bcur = (int)(idx / a.nk);
+    {
+      const int64_t k = a.k0 + (idx - (int64_t)bcur * a.nk);
+      valid = valid && (k >= a.H) && (k < a.N - a.H);   // interior samples only
+    }
+    const double* Yi = a.Y + idx;
+    const size_t BK = (size_t)a.BK;
+
+    // ---- one prefetch phase per tile: the A-shape correlations of every separable hypothesis and the
+    // correlations of every dense hypothesis go straight from global into this thread's shared-memory slice
+    // (cp.async, no registers); only the B shapes of separable hypotheses are streamed through registers,
+    // one run ahead.  Slice row of shape s: a.shrow[s] (or -1).
+    __syncwarp();
+    for (int sidx = 0; sidx < a.S; sidx++) {
+      const int row = sRow[sidx];
+      if (row >= 0) cp_async_f64(aY + 8u * EPI2_TPB * (unsigned)row, Yi + (size_t)sidx * BK);
+    }
+    cp_async_commit();
+
+    // ---------------- linear pass ----------------
+    double num = 0.0, den = 0.0;
+    unsigned kmax = 0;
+    bool big = false;
+    bool waited = false;
+    for (int h = 0; h < a.nhyp; h++) {
+      const int nB = a.hyp_nB[h];
+      if (nB <= 0) continue;
+      const int nA = a.hyp_nA[h], B0 = a.hyp_B0[h];
+      const bool half = a.hyp_half[h] != 0;
+      double S = 0.0;
+      const double* YB = Yi + (size_t)B0 * BK;
+      if (half && nA > 0) {
+        // B shapes in order, the next one prefetched while the pairs of the current run are evaluated
+        double yBn = __ldg(YB);
+        if (!waited) { cp_async_wait_all(); waited = true; }
+        const unsigned ayh = aY + 8u * EPI2_TPB * (unsigned)sRow[a.hyp_A0[h]];
+        unsigned ar = aRun + 8u * (unsigned)B0;
+        for (int ib = 0; ib < nB; ib++, ar += 8u) {
+          const double yB = yBn;
+          if (ib + 1 < nB) YB += BK;
+          yBn = __ldg(YB);
+          const int2 run = lds_b32x2(ar);
+          unsigned ap = aTP + (unsigned)run.x;
+          for (int p = 0; p < run.y; p++, ap += 48u) {
+            const double2 in = lds_f64x2(ap);              // (inorm0, inorm1)
+            const double2 cc = lds_f64x2(ap + 16u);        // (c0, c1)
+            const int2 fa = lds_b32x2(ap + 40u);           // (aoff0, aoff1)
+            const double y0 = lds_f64(ayh + (unsigned)fa.x), y1 = lds_f64(ayh + (unsigned)fa.y);
+            exphi2_pair(fma(in.x, y0 + yB, ZC), fma(in.y, y1 + yB, ZC), aT, cc.x, cc.y, S, kmax);
+          }
+        }
+      } else if (half && nA == 0) {
+        // dense hypothesis: consecutive templates in pairs, each with its own (prefetched) shape correlation
+        if (!waited) { cp_async_wait_all(); waited = true; }
+        const int2 run = lds_b32x2(aRun + 8u * (unsigned)B0);
+        unsigned ap = aTP + (unsigned)run.x;
+        unsigned ay = aY + 8u * EPI2_TPB * (unsigned)sRow[B0];
+        for (int ib = 0; ib < nB; ib += 2, ap += 48u, ay += 16u * EPI2_TPB) {
+          const double z0 = lds_f64(ay), z1 = lds_f64(ay + ((ib + 1 < nB) ? 8u * EPI2_TPB : 0u));
+          const double2 cc = lds_f64x2(ap + 16u);
+          exphi2_pair(z0 + ZC, z1 + ZC, aT, cc.x, cc.y, S, kmax);
+        }
+      } else {
+        // full-range amplitude: exp(z^2/2 - ZC^2/2), no table (also separable full-range hypotheses, unpaired)
+        if (!waited) { cp_async_wait_all(); waited = true; }
+        const unsigned ayh = aY + 8u * EPI2_TPB * (unsigned)((nA > 0) ? sRow[a.hyp_A0[h]] : 0);
+        for (int ib = 0; ib < nB; ib++) {
+          const double yB = (nA > 0) ? __ldg(YB + (size_t)ib * BK) : lds_f64(aY + 8u * EPI2_TPB * (unsigned)sRow[B0 + ib]);
+          const int g0 = sG01[2 * (B0 + ib)], g1 = sG01[2 * (B0 + ib) + 1];
+          for (int g = g0; g < g1; g++) {
+            const EpiTC tc = sTC[g];
+            const double z = (nA > 0) ? tc.inorm * (lds_f64(ayh + 8u * (unsigned)tc.aoff) + yB) : yB;
+            big = big || ((__double2hiint(z) & 0x7fffffff) >= 0x40180000);   // |z| >= 6 (or NaN)
+            S = fma(tc.c, exp_nonpos_poly(fma(0.5 * z, z, -0.5 * ZC * ZC)), S);
+          }
+        }
+      }
+      if (h == 0) num = S;
+      else den += S;
+    }
+    if (!waited) cp_async_wait_all();
+    big = big || (kmax > (unsigned)(BFL_EXPHI2_NI - 1));   // some |z| > ZC: redo in the log domain
+    double lnO = lnO_off + log(num / fma(w_poly, a.sqrtu[bcur], den));
+
+    // ---------------- log-domain pass (rare) ----------------
+    if (big) {
+      double mx = LSE_EMPTY, sm = 0.0, n_m = LSE_EMPTY, n_s = 0.0;
+      double d_m = a.noisepoly ? 0.0 : LSE_EMPTY, d_s = a.noisepoly ? 1.0 : 0.0;
+      const double hlv = a.halflogv[bcur];
+      for (int h = 0; h < a.nhyp; h++) {
+        const int nB = a.hyp_nB[h];
+        if (nB <= 0) continue;
+        const int nA = a.hyp_nA[h], B0 = a.hyp_B0[h];
+        const bool half = a.hyp_half[h] != 0;
+        const unsigned ayh = aY + 8u * EPI2_TPB * (unsigned)((nA > 0) ? sRow[a.hyp_A0[h]] : 0);
+        for (int ib = 0; ib < nB; ib++) {
+          const double yB = __ldg(Yi + (size_t)(B0 + ib) * BK);
+          const int g0 = sG01[2 * (B0 + ib)], g1 = sG01[2 * (B0 + ib) + 1];
+          for (int g = g0; g < g1; g++) {
+            const EpiTC tc = sTC[g];
+            const double z = (nA > 0) ? tc.inorm * (lds_f64(ayh + 8u * (unsigned)tc.aoff) + yB) : yB;
+            const double kg = sK[g];
+            double val;
+            if (half) val = kg + ((z < BFL_PHI_ZFAR) ? phi_half_far(z) : phi_tab_rows(z, BFL_PHI_TAB));
+            else val = fma(0.5 * z, z, kg);
+            lse_push_poly(mx, sm, val);
+          }
+        }
+        const double x = mx + ((half ? 0.5 * (BFL_LNPI - BFL_LN2) : 0.5 * (BFL_LN2 + BFL_LNPI)) + hlv);
+        if (h == 0) { n_m = x; n_s = sm; }
+        else {
+          const double d = x - d_m;
+          const double e = exp_nonpos_poly(-fabs(d));
+          const bool up = d > 0.0;
+          d_s = up ? fma(d_s, e, sm) : fma(sm, e, d_s);
+          d_m = up ? x : d_m;
+        }
+        mx = LSE_EMPTY; sm = 0.0;
+      }
+      lnO = (n_m - d_m) + log(n_s / d_s);
+    }
+    if (valid) a.lnO[idx] = lnO;
+  }
+}
+
+static int epi2_srows(const PlanView& pv) {
+  int r = 0;
+  for (int h = 0; h < pv.nhyp; h++) r += (pv.hyp_nA[h] > 0) ? pv.hyp_nA[h] : pv.hyp_nB[h];
+  return r;
+}
+static size_t epi2_smem_bytes(int G, int S, int srows) {
+  return sizeof(double) * (size_t)(BFL_EXPHI2_NI + 1) + sizeof(EpiTP) * (size_t)(G / 2 + S + 1) + sizeof(EpiTC) * (size_t)G +
+         sizeof(double) * ((size_t)((G + 1) & ~1) + MAXH + 2 + MAXH + 2 + (size_t)srows * EPI2_TPB) + sizeof(int) * (size_t)(5 * S + 2);
+}
+
 static size_t corr_smem_bytes(int S, int KT) {
   const int wstride = (32 * KT + 2 * 27 + 2) & ~1;
   return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)S * 56);
@@ -1075,7 +1467,7 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   if (e != cudaSuccess) return e;
 
   EpiArgs a;
-  a.Y = sc.Y; a.halflogv = sc.halflogv; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
+  a.Y = sc.Y; a.halflogv = sc.halflogv; a.sqrtu = sc.sqrtu; a.tile_counter = sc.tile_counters + 1; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
   a.B = sv.B; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
   for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
   for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
@@ -1097,6 +1489,24 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
     if (gx > ntiles) gx = ntiles;                                                                           \
     k_epilogue<MODE_, SPT><<<(unsigned)(gx < 1 ? 1 : gx), EPI_TPB, smem2, s>>>(a);                          \
   } while (0)
+  static int epi_version = -1;   // BFL_EPI=1 selects the round-1 all-fp64 evaluation (kept for A/B measurements)
+  if (epi_version < 0) { const char* ev = getenv("BFL_EPI"); epi_version = (ev && atoi(ev) == 1) ? 1 : 2; }
+  a.srows = epi2_srows(pv);
+  // one sample per thread needs the whole per-thread slice in shared memory four times per SM: small plans only
+  if (epi_version == 2 && mode == 2 && epi2_smem_bytes(pv.G, pv.S, a.srows) <= 56 * 1024) {
+    const size_t smem3 = epi2_smem_bytes(pv.G, pv.S, a.srows);
+    e = cudaFuncSetAttribute(k_epilogue2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_epilogue2, EPI2_TPB, smem3);
+    if (e != cudaSuccess) return e;
+    int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);
+    const int64_t ntiles2 = (a.BK + EPI2_TPB - 1) / EPI2_TPB;   // CTA-sized groups of warp tiles
+    if (gx > ntiles2) gx = ntiles2;
+    k_epilogue2<<<(unsigned)(gx < 1 ? 1 : gx), EPI2_TPB, smem3, s>>>(a);
+    st->launches++;
+    return cudaGetLastError();
+  }
   if (mode == 2) BFL_EPI(2); else BFL_EPI(0);
 #undef BFL_EPI
   st->launches++;

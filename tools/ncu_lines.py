@@ -4,10 +4,11 @@
 """
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+units = float(sys.argv[2]) if len(sys.argv) > 2 and float(sys.argv[2]) > 0 else None
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # which profiled launch of the report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, r = rows[0], rows[2]
+hdr, r = rows[0], rows[2 + kidx]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
         'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -29,13 +30,25 @@ for v, h in sorted(st, reverse=True)[:7]:
     print("%-75s %.3f" % (h, v))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = rows[2]; iS = h.index('# Samples'); iI = h.index('Instructions Executed')
-body = []
-for x in rows[3:]:
-    if x and x[0] == "Line No":
-        break
+# the page is a sequence of per-file tables; a launch starts at each table of our own .cu file
+secs = [i for i, x in enumerate(rows) if x and x[0] == "File Path"]
+mine = [i for i in secs if rows[i][1].endswith(".cu")]
+lo = mine[min(kidx, len(mine) - 1)]
+hi = mine[kidx + 1] if kidx + 1 < len(mine) else len(rows)
+h = rows[lo + 2]; iS = h.index('# Samples'); iI = h.index('Instructions Executed')
+body, other = [], [0, 0]
+cur_mine = True
+for i in range(lo, hi):
+    x = rows[i]
+    if x and x[0] == "File Path":
+        cur_mine = x[1].endswith(".cu")
+        continue
     if len(x) > iI and x[0].isdigit() and x[iS].isdigit():
-        body.append(x)
+        if cur_mine:
+            body.append(x)
+        else:
+            other[0] += int(x[iS]); other[1] += int(x[iI])
+print("\n(samples / instructions attributed to inlined CUDA header lines: %d / %d)" % tuple(other))
 tot = sum(int(x[iS]) for x in body); totI = sum(int(x[iI]) for x in body)
 agg = {}
 for x in body:
