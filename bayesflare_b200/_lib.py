@@ -31,6 +31,14 @@ class Hypothesis(C.Structure):
                 ("params", _dp), ("logprior", _dp), ("logweight", _dp), ("table", _dp)]
 
 
+class Region(C.Structure):
+    _fields_ = [("curve", C.c_int32), ("start", C.c_int32), ("stop", C.c_int32), ("argmax", C.c_int32),
+                ("maxval", C.c_double)]
+
+
+REGION_DTYPE = np.dtype([("curve", "<i4"), ("start", "<i4"), ("stop", "<i4"), ("argmax", "<i4"), ("maxval", "<f8")])
+
+
 class NoiseSpec(C.Structure):
     _fields_ = [("method", C.c_int32), ("bglen", C.c_int32), ("param", C.c_double), ("sgcoef", _dp)]
 
@@ -89,6 +97,13 @@ SIGNATURES = {
     "bfl_detector_odds_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_void_p]),
+    "bfl_pipe_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(NoiseSpec), C.c_int32, C.c_int64, C.c_int64,
+                                  C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bfl_pipe_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, _i64p]),
+    "bfl_pipe_wait": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
+    "bfl_pipe_launch_count": (C.c_int64, [C.c_void_p]),
+    "bfl_pipe_destroy": (C.c_int, [C.c_void_p]),
     "bfl_threshold": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_double, C.c_int32, _i64p, _dp, _i64p, C.c_int32,
                                 C.POINTER(C.c_int32)]),
     "bfl_pe_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, C.c_int64, C.c_int32,
@@ -301,15 +316,60 @@ class Plan:
             out = out + (sk_out,)
         return out if len(out) > 1 else out[0]
 
-    def detector_odds_dev(self, d_clc, d_cle, const_var, d_sk, B, N, seg0, seglen, k0, k1, d_lnO, noisepoly=True):
-        """Device-resident, asynchronous variant: arguments are raw device addresses (ints)."""
-        check(self.lib.bfl_detector_odds_dev(self.ctx.handle, self.handle, 1 if noisepoly else 0, d_clc, d_cle or None,
+    def detector_odds_dev(self, d_clc, d_cle, const_var, d_sk, B, N, seg0, seglen, k0, k1, d_lnO, noisepoly=True, ctx=None):
+        """Device-resident, asynchronous variant: arguments are raw device addresses (ints).  ``ctx``: run on
+        another context of the same device (its stream, its scratch) -- the plan itself is read-only."""
+        check(self.lib.bfl_detector_odds_dev((ctx or self.ctx).handle, self.handle, 1 if noisepoly else 0, d_clc, d_cle or None,
                                              1 if const_var else 0, d_sk, int(B), int(N), int(seg0), int(seglen),
                                              int(k0), int(k1), d_lnO))
 
     def close(self):
         if getattr(self, "handle", None):
             self.lib.bfl_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipe:
+    """``bfl_pipe``: asynchronous batch search.  ``submit`` takes raw host addresses (ints, e.g. of page-locked
+    torch / NumPy buffers that the caller keeps alive) and returns a job number; ``wait`` blocks until that
+    job's outputs are in host memory and returns the number of region records."""
+
+    def __init__(self, plan, B, N, k0, k1, noise=None, noisepoly=True, depth=3, max_regions=None):
+        self.plan, self.lib = plan, plan.lib
+        self.B, self.N, self.k0, self.k1 = int(B), int(N), int(k0), int(k1)
+        self.max_regions = int(8 * B if max_regions is None else max_regions)
+        self._noise = noise          # keeps the coefficient array alive
+        h = C.c_void_p()
+        check(self.lib.bfl_pipe_create(plan.ctx.handle, plan.handle, 1 if noisepoly else 0,
+                                       C.byref(noise[0]) if noise is not None else None, self.B, self.N, self.k0, self.k1,
+                                       int(depth), self.max_regions, C.byref(h)))
+        self.handle = h
+
+    def submit(self, clc_addr, sk_addr=None, out_lnO_addr=None, thresh=float("nan"), out_regions_addr=None,
+               out_counts_addr=None, out_sk_addr=None):
+        job = C.c_int64(-1)
+        check(self.lib.bfl_pipe_submit(self.handle, clc_addr, sk_addr, out_lnO_addr, float(thresh), out_regions_addr,
+                                       out_counts_addr, out_sk_addr, C.byref(job)))
+        return job.value
+
+    def wait(self, job):
+        n = C.c_int32(0)
+        check(self.lib.bfl_pipe_wait(self.handle, int(job), C.byref(n)))
+        return n.value
+
+    @property
+    def launches(self):
+        return int(self.lib.bfl_pipe_launch_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.bfl_pipe_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -452,6 +452,17 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
   pv.raw = (const double*)d_raw; pv.hat = (const double*)d_hat; pv.Kg = (const double*)d_Kg;
   pv.lp = (const double*)d_lp; pv.lw = (const double*)d_lw; pv.gorig = (const int*)d_gorig;
   pv.bg = (const double*)d_bg; pv.bb = (const double*)d_bb; pv.qb = (const double*)d_qb;
+  pv.epi2_block[0] = pv.epi2_block[1] = nullptr;
+  if (epi2_fits(pv)) {
+    for (int np = 0; np < 2; np++) {
+      void* blk = nullptr;
+      if ((rc = plan_alloc(p, epi2_plan_block_bytes(pv), &blk))) { bfl_plan_destroy(p); return rc; }
+      cudaError_t e = launch_epilogue2_prepare(pv, np, blk, s, &c->stats);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { bfl_plan_destroy(p); return fail(BFL_ERR_CUDA, std::string("k_epilogue2_prepare: ") + cudaGetErrorString(e)); }
+      pv.epi2_block[np] = blk;
+    }
+  }
   *out = p;
   return BFL_OK;
 }
@@ -754,6 +765,148 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
   if (out_marg) CK(cudaMemcpyAsync(out_marg, d_marg, nbo * (size_t)(p->pv.nhyp + 1), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return BFL_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// Pipelined batch search: bfl_pipe.  Every slot owns a child context (its own stream and scratch), so the
+// host->device copy of job i+1, the kernels of job i and the device->host copy of job i-1 overlap, and the tail
+// of one job's kernels is filled by the next job's.  The plan is shared (read-only on the device).
+static_assert(sizeof(bfl_region) == sizeof(RegionRec), "bfl_region and RegionRec must have one layout");
+struct bfl_pipe {
+  bfl_ctx* parent = nullptr;
+  bfl_plan* plan = nullptr;
+  int noisepoly = 1;
+  bool have_noise = false;
+  bfl_noise_spec noise{};
+  std::vector<double> sgcoef;
+  int32_t B = 0, max_regions = 0;
+  int64_t N = 0, k0 = 0, k1 = 0;
+  struct Slot {
+    bfl_ctx* ctx = nullptr;
+    double *d_clc = nullptr, *d_sk = nullptr, *d_lnO = nullptr;
+    RegionRec* d_rec = nullptr;
+    int64_t* d_cnt = nullptr;        // [B + 3]
+    cudaEvent_t done = nullptr;
+    int64_t job = -1;
+    const int64_t* host_cnt = nullptr;
+  };
+  std::vector<Slot> slots;
+  int64_t submitted = 0;
+};
+
+int bfl_pipe_destroy(bfl_pipe* p) {
+  if (!p) return BFL_OK;
+  if (p->parent) cudaSetDevice(p->parent->device);
+  for (auto& sl : p->slots) {
+    if (sl.ctx) cudaStreamSynchronize(sl.ctx->stream);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.d_clc) cudaFree(sl.d_clc);
+    if (sl.d_sk) cudaFree(sl.d_sk);
+    if (sl.d_lnO) cudaFree(sl.d_lnO);
+    if (sl.d_rec) cudaFree(sl.d_rec);
+    if (sl.d_cnt) cudaFree(sl.d_cnt);
+    if (sl.ctx) bfl_ctx_destroy(sl.ctx);
+  }
+  delete p;
+  return BFL_OK;
+}
+
+int bfl_pipe_create(bfl_ctx* c, bfl_plan* plan, int noisepoly, const bfl_noise_spec* noise, int32_t B, int64_t N,
+                    int64_t k0, int64_t k1, int32_t depth, int32_t max_regions, bfl_pipe** out) {
+  if (!c || !plan || !out) return fail(BFL_ERR_ARG, "null argument to bfl_pipe_create");
+  *out = nullptr;
+  if (B < 1 || N < plan->pv.W || k0 < 0 || k1 > N || k0 >= k1) return fail(BFL_ERR_ARG, "bad batch shape or sample range");
+  if (depth < 1 || depth > 8) return fail(BFL_ERR_ARG, "pipeline depth must be in 1..8");
+  if (max_regions < 0) return fail(BFL_ERR_ARG, "max_regions must not be negative");
+  CK(cudaSetDevice(c->device));
+  bfl_pipe* p = new (std::nothrow) bfl_pipe();
+  if (!p) return fail(BFL_ERR_OOM, "out of host memory");
+  p->parent = c; p->plan = plan; p->noisepoly = noisepoly ? 1 : 0;
+  p->B = B; p->N = N; p->k0 = k0; p->k1 = k1; p->max_regions = max_regions;
+  if (noise) {
+    p->have_noise = true;
+    p->noise = *noise;
+    if (noise->sgcoef && noise->bglen > 0) {
+      p->sgcoef.assign(noise->sgcoef, noise->sgcoef + noise->bglen);
+      p->noise.sgcoef = p->sgcoef.data();
+    }
+  }
+  const size_t nb = sizeof(double) * (size_t)B * N, nbo = sizeof(double) * (size_t)B * (size_t)(k1 - k0);
+  p->slots.resize(depth);
+  for (auto& sl : p->slots) {
+    int rc = bfl_ctx_create(c->device, nullptr, &sl.ctx);
+    if (rc) { bfl_pipe_destroy(p); return rc; }
+    cudaError_t e = cudaMalloc(&sl.d_clc, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_sk, sizeof(double) * (size_t)B);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_lnO, nbo);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_rec, sizeof(RegionRec) * (size_t)std::max(max_regions, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_cnt, sizeof(int64_t) * (size_t)(B + 3));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      bfl_pipe_destroy(p);
+      return fail(e == cudaErrorMemoryAllocation ? BFL_ERR_OOM : BFL_ERR_CUDA, std::string("bfl_pipe_create: ") + cudaGetErrorString(e));
+    }
+  }
+  *out = p;
+  return BFL_OK;
+}
+
+int bfl_pipe_submit(bfl_pipe* p, const double* clc, const double* sk, double* out_lnO, double thresh,
+                    bfl_region* out_regions, int64_t* out_counts, double* out_sk, int64_t* job) {
+  if (!p || !clc) return fail(BFL_ERR_ARG, "null argument to bfl_pipe_submit");
+  if (!sk && !p->have_noise) return fail(BFL_ERR_ARG, "either the noise sigmas or a noise specification is required");
+  const bool want_regions = !std::isnan(thresh);
+  if (want_regions && !out_counts) return fail(BFL_ERR_ARG, "out_counts is required when a threshold is given");
+  if (!want_regions && !out_lnO) return fail(BFL_ERR_ARG, "nothing to return: give out_lnO and/or a threshold");
+  CK(cudaSetDevice(p->parent->device));
+  bfl_pipe::Slot& sl = p->slots[(size_t)(p->submitted % (int64_t)p->slots.size())];
+  if (sl.job >= 0) CK(cudaEventSynchronize(sl.done));   // the slot's previous job must have left the device
+  bfl_ctx* c = sl.ctx;
+  cudaStream_t s = c->stream;
+  const int32_t B = p->B;
+  const int64_t N = p->N, nk = p->k1 - p->k0;
+  int rc;
+  CK(cudaMemcpyAsync(sl.d_clc, clc, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, s));
+  if (sk) CK(cudaMemcpyAsync(sl.d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+  else if ((rc = noise_run(c, &p->noise, sl.d_clc, B, N, sl.d_sk))) return rc;
+  SeriesView sv{sl.d_clc, nullptr, sl.d_sk, B, N, 0, N, p->k0, p->k1, 1};
+  if ((rc = detector_run(c, p->plan, p->noisepoly, sv, sl.d_lnO, nullptr))) return rc;
+  if (out_sk) CK(cudaMemcpyAsync(out_sk, sl.d_sk, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  if (want_regions) {
+    CK(cudaMemsetAsync(sl.d_cnt, 0, sizeof(int64_t) * (size_t)(B + 3), s));
+    CK(launch_batch_regions(sl.d_lnO, B, nk, thresh, sl.d_rec, p->max_regions, sl.d_cnt, sl.d_cnt + B, s, &c->stats));
+    CK(cudaMemcpyAsync(out_counts, sl.d_cnt, sizeof(int64_t) * (size_t)(B + 3), cudaMemcpyDeviceToHost, s));
+    if (out_regions && p->max_regions > 0)
+      CK(cudaMemcpyAsync(out_regions, sl.d_rec, sizeof(RegionRec) * (size_t)p->max_regions, cudaMemcpyDeviceToHost, s));
+  }
+  if (out_lnO) CK(cudaMemcpyAsync(out_lnO, sl.d_lnO, sizeof(double) * (size_t)B * (size_t)nk, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(sl.done, s));
+  sl.job = p->submitted;
+  sl.host_cnt = want_regions ? out_counts : nullptr;
+  if (job) *job = p->submitted;
+  p->submitted++;
+  return BFL_OK;
+}
+
+int bfl_pipe_wait(bfl_pipe* p, int64_t job, int32_t* nregions) {
+  if (!p) return fail(BFL_ERR_ARG, "null pipe");
+  if (nregions) *nregions = 0;
+  if (job < 0 || job >= p->submitted) return fail(BFL_ERR_ARG, "no such job");
+  if (job < p->submitted - (int64_t)p->slots.size()) return BFL_OK;   // its slot was reused: it completed long ago
+  bfl_pipe::Slot& sl = p->slots[(size_t)(job % (int64_t)p->slots.size())];
+  CK(cudaEventSynchronize(sl.done));
+  if (nregions && sl.host_cnt) {
+    const int64_t n = sl.host_cnt[p->B + 2];
+    if (n > p->max_regions) return fail(BFL_ERR_UNSUPPORTED, "more regions than max_regions (out_counts is complete; raise max_regions)");
+    *nregions = (int32_t)n;
+  }
+  return BFL_OK;
+}
+
+int64_t bfl_pipe_launch_count(const bfl_pipe* p) {
+  int64_t n = 0;
+  if (p) for (auto& sl : p->slots) n += sl.ctx ? sl.ctx->stats.launches : 0;
+  return n;
 }
 
 // --------------------------------------------------------------------------------------

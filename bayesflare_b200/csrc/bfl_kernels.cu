@@ -790,6 +790,7 @@ struct EpiArgs {
   const double* halflogv; // [B]
   const double* sqrtu;    // [B]
   unsigned long long* tile_counter;   // k_epilogue2: next warp tile (zeroed by k_prep_scalars)
+  const unsigned char* plan_block;    // k_epilogue2: per-plan shared-memory block built by k_epilogue2_prepare
   int srows;              // k_epilogue2: rows of the per-thread slice (A shapes of separable + all shapes of dense hypotheses)
   int64_t nk, BK, N, k0;
   int B, G, nhyp, H;
@@ -1165,23 +1166,45 @@ __device__ __forceinline__ double f64_from_order_key(long long k) {
 // with E_h = exp(phi) for half-range amplitudes (exphi2_pair) and exp(z^2/2 - ZC^2/2) for full-range ones.
 // LOG pass (only threads that met |z| > ZC, i.e. a flare or a deep dip): phi table + online log-sum-exp per
 // hypothesis, any z, as k_epilogue does.
-__global__ void __launch_bounds__(EPI2_TPB, BFL_EPI2_MINB) k_epilogue2(const EpiArgs a) {
+// shared-memory layout of k_epilogue2: [per-plan block, identical in every CTA and every launch][per-thread slice]
+struct Epi2Layout {
+  int oT, oTP, oTC, oK, oCref, oConst, oG01, oRun, oRow, plan_bytes;   // byte offsets; plan_bytes is a multiple of 16
+  __host__ __device__ Epi2Layout(int G, int S) {
+    int o = 0;
+    oT = o; o += 8 * (BFL_EXPHI2_NI + 1);
+    oTP = o; o += (int)sizeof(EpiTP) * (G / 2 + S + 1);
+    oTC = o; o += (int)sizeof(EpiTC) * G;
+    oK = o; o += 8 * ((G + 1) & ~1);
+    oCref = o; o += 8 * MAXH;
+    oConst = o; o += 8 * 2;
+    oG01 = o; o += 8 * S;
+    oRun = o; o += 8 * S;
+    oRow = o; o += 4 * S;
+    plan_bytes = (o + 15) & ~15;
+  }
+};
+
+// Builds the per-plan block ONCE per (plan, noisepoly) -- at plan creation, not in every CTA of every launch
+// (at 128 light curves per GPU the 592 CTA prologues were a tenth of the kernel): one CTA, result in global memory.
+__global__ void __launch_bounds__(EPI2_TPB) k_epilogue2_prepare(const EpiArgs a, unsigned char* __restrict__ blob) {
   extern __shared__ double smem[];
+  unsigned char* sb = reinterpret_cast<unsigned char*>(smem);
   const int tid = threadIdx.x;
   const int G = a.G;
-  const int npairs_max = G / 2 + a.S + 1;
-  double* sT = smem;                                                   // [NI + 1] E_k
-  EpiTP* sTP = reinterpret_cast<EpiTP*>(sT + BFL_EXPHI2_NI + 1);       // [npairs_max]
-  EpiTC* sTC = reinterpret_cast<EpiTC*>(sTP + npairs_max);             // [G]  (full-range and log-domain loops)
-  double* sK = reinterpret_cast<double*>(sTC + G);                     // [G] Kg + lp + lw
-  double* sCref = sK + ((G + 1) & ~1);                                 // [MAXH] per-hypothesis maximum of sK (log pass)
-  double* sConst = sCref + MAXH;                                       // [2] lnO offset, weight of the polynomial-only model
-  long long* sKey = reinterpret_cast<long long*>(sConst + 2);          // [MAXH + 2] maxima under construction
-  double* ysm = reinterpret_cast<double*>(sKey + MAXH + 2);            // [srows][EPI2_TPB]
-  int* sG01 = reinterpret_cast<int*>(ysm + (size_t)a.srows * EPI2_TPB);   // [S][2] run of templates per B shape
-  int2* sRun = reinterpret_cast<int2*>(sG01 + 2 * a.S);                // [S] (byte offset of the run's first pair, pairs)
-  int* sRow = reinterpret_cast<int*>(sRun + a.S);                      // [S] row of shape s in the thread slice, or -1
+  const Epi2Layout L(G, a.S);
+  double* sT = reinterpret_cast<double*>(sb + L.oT);                   // [NI + 1] E_k
+  EpiTP* sTP = reinterpret_cast<EpiTP*>(sb + L.oTP);                   // [G / 2 + S + 1]
+  EpiTC* sTC = reinterpret_cast<EpiTC*>(sb + L.oTC);                   // [G]  (full-range and log-domain loops)
+  double* sK = reinterpret_cast<double*>(sb + L.oK);                   // [G] Kg + lp + lw
+  double* sCref = reinterpret_cast<double*>(sb + L.oCref);             // [MAXH] per-hypothesis maximum of sK (log pass)
+  double* sConst = reinterpret_cast<double*>(sb + L.oConst);           // [2] lnO offset, weight of the polynomial-only model
+  int* sG01 = reinterpret_cast<int*>(sb + L.oG01);                     // [S][2] run of templates per B shape
+  int2* sRun = reinterpret_cast<int2*>(sb + L.oRun);                   // [S] (byte offset of the run's first pair, pairs)
+  int* sRow = reinterpret_cast<int*>(sb + L.oRow);                     // [S] row of shape s in the thread slice, or -1
+  long long* sKey = reinterpret_cast<long long*>(sb + L.plan_bytes);   // [MAXH + 2] maxima under construction
   constexpr double ZC = BFL_EXPHI2_ZC;
+  for (int i = tid; i < L.plan_bytes / 8; i += EPI2_TPB) smem[i] = 0.0;
+  __syncthreads();
   for (int i = tid; i < G; i += EPI2_TPB) sK[i] = a.Kg[i] + a.lp[i] + a.lw[i];
   for (int i = tid; i < a.S; i += EPI2_TPB) { sG01[2 * i] = a.sh_g0[i]; sG01[2 * i + 1] = a.sh_g1[i]; }
   for (int i = tid; i < BFL_EXPHI2_NI; i += EPI2_TPB) sT[i] = BFL_EXPHI2_TAB[i];
@@ -1258,6 +1281,28 @@ __global__ void __launch_bounds__(EPI2_TPB, BFL_EPI2_MINB) k_epilogue2(const Epi
       sTP[sRun[sB].x / 48 + loc / 2] = tp;
     }
   }
+  __syncthreads();
+  for (int i = tid; i < L.plan_bytes / 16; i += EPI2_TPB)
+    reinterpret_cast<uint4*>(blob)[i] = reinterpret_cast<const uint4*>(sb)[i];
+}
+
+__global__ void __launch_bounds__(EPI2_TPB, BFL_EPI2_MINB) k_epilogue2(const EpiArgs a) {
+  extern __shared__ double smem[];
+  unsigned char* sb = reinterpret_cast<unsigned char*>(smem);
+  const int tid = threadIdx.x;
+  const Epi2Layout L(a.G, a.S);
+  for (int i = tid; i < L.plan_bytes / 16; i += EPI2_TPB)
+    reinterpret_cast<uint4*>(sb)[i] = __ldg(reinterpret_cast<const uint4*>(a.plan_block) + i);
+  double* sT = reinterpret_cast<double*>(sb + L.oT);
+  EpiTP* sTP = reinterpret_cast<EpiTP*>(sb + L.oTP);
+  EpiTC* sTC = reinterpret_cast<EpiTC*>(sb + L.oTC);
+  double* sK = reinterpret_cast<double*>(sb + L.oK);
+  double* sConst = reinterpret_cast<double*>(sb + L.oConst);
+  int* sG01 = reinterpret_cast<int*>(sb + L.oG01);
+  int2* sRun = reinterpret_cast<int2*>(sb + L.oRun);
+  int* sRow = reinterpret_cast<int*>(sb + L.oRow);
+  double* ysm = reinterpret_cast<double*>(sb + L.plan_bytes);          // [srows][EPI2_TPB] per-thread slice
+  constexpr double ZC = BFL_EXPHI2_ZC;
   __syncthreads();
   const unsigned aT = (unsigned)__cvta_generic_to_shared(sT);
   const unsigned aTP = (unsigned)__cvta_generic_to_shared(sTP);
@@ -1408,9 +1453,13 @@ static int epi2_srows(const PlanView& pv) {
   return r;
 }
 static size_t epi2_smem_bytes(int G, int S, int srows) {
-  return sizeof(double) * (size_t)(BFL_EXPHI2_NI + 1) + sizeof(EpiTP) * (size_t)(G / 2 + S + 1) + sizeof(EpiTC) * (size_t)G +
-         sizeof(double) * ((size_t)((G + 1) & ~1) + MAXH + 2 + MAXH + 2 + (size_t)srows * EPI2_TPB) + sizeof(int) * (size_t)(5 * S + 2);
+  return (size_t)Epi2Layout(G, S).plan_bytes + sizeof(double) * (size_t)srows * EPI2_TPB;
 }
+bool epi2_fits(const PlanView& pv) {   // one sample per thread: the slice must fit four times per SM
+  return pv.sep_ok && pv.wsep_ok && pv.W == 55 && pv.G > 0 && pv.nhyp >= 1 && pv.hyp_begin[1] > 0 &&
+         epi2_smem_bytes(pv.G, pv.S, epi2_srows(pv)) <= 56 * 1024;
+}
+size_t epi2_plan_block_bytes(const PlanView& pv) { return (size_t)Epi2Layout(pv.G, pv.S).plan_bytes; }
 
 static size_t corr_smem_bytes(int S, int KT) {
   const int wstride = (32 * KT + 2 * 27 + 2) & ~1;
@@ -1432,6 +1481,33 @@ bool fast_split_fits(const PlanView& pv) {
   if (off < 0) { const char* e = getenv("BFL_NO_SPLIT"); off = (e && atoi(e)) ? 1 : 0; }
   return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && pv.wsep_ok &&
          epi_smem_bytes(pv.G, pv.S, epi_arows(pv), BFL_EPI_SPT) <= 50 * 1024 * BFL_EPI_SPT;   // wsep_ok: templates grouped by B shape
+}
+
+static void fill_epi_plan_args(EpiArgs& a, const PlanView& pv, int noisepoly) {
+  a.Y = nullptr; a.halflogv = nullptr; a.sqrtu = nullptr; a.tile_counter = nullptr; a.plan_block = nullptr;
+  a.nk = a.BK = a.N = a.k0 = 0; a.B = 0; a.lnO = nullptr; a.part = nullptr;
+  a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
+  for (int h = 0; h <= MAXH; h++) a.hyp_begin[h] = (h <= pv.nhyp) ? pv.hyp_begin[h] : pv.hyp_begin[pv.nhyp];
+  for (int h = 0; h < MAXH; h++) {
+    const bool on = h < pv.nhyp;
+    a.hyp_half[h] = on ? pv.hyp_half[h] : 0; a.hyp_A0[h] = on ? pv.hyp_A0[h] : 0; a.hyp_nA[h] = on ? pv.hyp_nA[h] : 0;
+    a.hyp_B0[h] = on ? pv.hyp_B0[h] : 0; a.hyp_nB[h] = on ? pv.hyp_nB[h] : 0;
+  }
+  a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
+  a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = epi_arows(pv); a.srows = epi2_srows(pv);
+  a.noisepoly = noisepoly;
+}
+
+// per-plan shared-memory block of k_epilogue2 for one value of noisepoly -> d_block (epi2_plan_block_bytes(pv) bytes)
+cudaError_t launch_epilogue2_prepare(const PlanView& pv, int noisepoly, void* d_block, cudaStream_t s, LaunchStats* st) {
+  EpiArgs a;
+  fill_epi_plan_args(a, pv, noisepoly);
+  const size_t smem = epi2_plan_block_bytes(pv) + sizeof(long long) * (MAXH + 2);
+  cudaError_t e = cudaFuncSetAttribute(k_epilogue2_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_epilogue2_prepare<<<1, EPI2_TPB, smem, s>>>(a, (unsigned char*)d_block);
+  st->launches++;
+  return cudaGetLastError();
 }
 
 // mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
@@ -1467,14 +1543,9 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   if (e != cudaSuccess) return e;
 
   EpiArgs a;
+  fill_epi_plan_args(a, pv, noisepoly);
   a.Y = sc.Y; a.halflogv = sc.halflogv; a.sqrtu = sc.sqrtu; a.tile_counter = sc.tile_counters + 1; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
-  a.B = sv.B; a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
-  for (int h = 0; h <= pv.nhyp; h++) a.hyp_begin[h] = pv.hyp_begin[h];
-  for (int h = 0; h < pv.nhyp; h++) { a.hyp_half[h] = pv.hyp_half[h]; a.hyp_A0[h] = pv.hyp_A0[h]; a.hyp_nA[h] = pv.hyp_nA[h]; }
-  for (int h = 0; h < pv.nhyp; h++) { a.hyp_B0[h] = pv.hyp_B0[h]; a.hyp_nB[h] = pv.hyp_nB[h]; }
-  a.Kg = pv.Kg; a.lp = pv.lp; a.lw = pv.lw; a.inorm = pv.inorm; a.idxA = pv.idxA; a.idxB = pv.idxB;
-  a.sh_g0 = pv.sh_g0; a.sh_g1 = pv.sh_g1; a.S = pv.S; a.arows = epi_arows(pv);
-  a.noisepoly = noisepoly; a.lnO = d_lnO; a.part = sc.part;
+  a.B = sv.B; a.lnO = d_lnO; a.part = sc.part;
   constexpr int SPT = BFL_EPI_SPT;
   const size_t smem2 = epi_smem_bytes(pv.G, pv.S, a.arows, SPT);
   const int64_t ntiles = (a.BK + EPI_TPB * SPT - 1) / (EPI_TPB * SPT);
@@ -1491,9 +1562,8 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   } while (0)
   static int epi_version = -1;   // BFL_EPI=1 selects the round-1 all-fp64 evaluation (kept for A/B measurements)
   if (epi_version < 0) { const char* ev = getenv("BFL_EPI"); epi_version = (ev && atoi(ev) == 1) ? 1 : 2; }
-  a.srows = epi2_srows(pv);
-  // one sample per thread needs the whole per-thread slice in shared memory four times per SM: small plans only
-  if (epi_version == 2 && mode == 2 && epi2_smem_bytes(pv.G, pv.S, a.srows) <= 56 * 1024) {
+  a.plan_block = (const unsigned char*)pv.epi2_block[noisepoly ? 1 : 0];
+  if (epi_version == 2 && mode == 2 && a.plan_block) {
     const size_t smem3 = epi2_smem_bytes(pv.G, pv.S, a.srows);
     e = cudaFuncSetAttribute(k_epilogue2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
     if (e != cudaSuccess) return e;
@@ -3068,6 +3138,44 @@ cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double t
   const int64_t tot = n * B;
   k_count_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts,
                                                                 (unsigned long long*)d_totals);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+// Regions of a whole batch in one launch (contiguous_regions, find.py:15-52, for every curve): the thread of a
+// sample that OPENS a region (above threshold, predecessor not) walks to its end -- regions are a few samples
+// long and rare -- and emits one record {curve, start, stop, argmax, max} (first maximum, as np.argmax);
+// per-curve counts and batch totals as k_count_regions.  Record order is arbitrary (atomic slot counter).
+__global__ void k_batch_regions(const double* __restrict__ lnO, int B, int64_t n, double thresh, RegionRec* recs, int cap,
+                                unsigned long long* counts, unsigned long long* totals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * B) return;
+  const int64_t b = i / n, k = i - b * n;
+  if (!(lnO[i] > thresh)) return;
+  if (k > 0 && lnO[i - 1] > thresh) return;
+  const double* row = lnO + b * n;
+  double best = row[k];
+  int64_t bi = k, e = k + 1;
+  while (e < n && row[e] > thresh) {
+    if (row[e] > best) { best = row[e]; bi = e; }
+    e++;
+  }
+  const unsigned long long before = atomicAdd(&counts[b], 1ULL);
+  atomicAdd(&totals[0], 1ULL);
+  if (before == 0ULL) atomicAdd(&totals[1], 1ULL);
+  const unsigned long long slot = atomicAdd(&totals[2], 1ULL);
+  if (slot < (unsigned long long)cap) {
+    RegionRec r;
+    r.curve = (int)b; r.start = (int)k; r.stop = (int)e; r.argmax = (int)bi; r.maxval = best;
+    recs[slot] = r;
+  }
+}
+
+cudaError_t launch_batch_regions(const double* d_lnO, int B, int64_t n, double thresh, RegionRec* d_recs, int cap,
+                                 int64_t* d_counts, int64_t* d_totals, cudaStream_t s, LaunchStats* st) {
+  const int64_t tot = n * B;
+  k_batch_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, d_recs, cap,
+                                                                (unsigned long long*)d_counts, (unsigned long long*)d_totals);
   st->launches++;
   return cudaGetLastError();
 }

@@ -54,6 +54,9 @@ struct PlanView {
   const int* sh_g1;
   int hyp_B0[MAXH];          // global shape index of the hypothesis' first B shape
   int hyp_nB[MAXH];          // number of B shapes
+  // ---- per-plan shared-memory block of k_epilogue2 (tables, per-template weights, run lists), built once at
+  // plan creation for noisepoly = 0 / 1; nullptr when the plan does not fit that kernel
+  const void* epi2_block[2];
 };
 
 constexpr int SEP_MAXA = 16;   // A shapes per hypothesis the kernel keeps per thread in shared memory
@@ -85,6 +88,9 @@ struct Scratch {
 };
 
 struct LaunchStats { int64_t launches = 0; };
+
+// one above-threshold region of one light curve (same layout as bfl_region in include/bfl.h)
+struct RegionRec { int32_t curve, start, stop, argmax; double maxval; };
 
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
                                  double* d_raw, cudaStream_t s, LaunchStats* st);
@@ -140,6 +146,8 @@ cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int ns
 
 cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
                                  int64_t* d_totals, cudaStream_t s, LaunchStats* st);
+cudaError_t launch_batch_regions(const double* d_lnO, int B, int64_t n, double thresh, RegionRec* d_recs, int cap,
+                                 int64_t* d_counts, int64_t* d_totals, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
                             cudaStream_t s, LaunchStats* st);
 cudaError_t launch_ps_sigma(const double2* d_X, int64_t N, int B, double estfrac, double* d_sk, cudaStream_t s,
@@ -156,6 +164,9 @@ cudaError_t launch_sweep_score(const double* d_lnO, int B, int64_t nk, int h, co
                                cudaStream_t s, LaunchStats* st);
 
 bool fast_split_fits(const PlanView& pv);
+bool epi2_fits(const PlanView& pv);
+size_t epi2_plan_block_bytes(const PlanView& pv);
+cudaError_t launch_epilogue2_prepare(const PlanView& pv, int noisepoly, void* d_block, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
                                 double* d_lnO, cudaStream_t s, LaunchStats* st);
 size_t fast_smem_bytes(int W, int gchunk, int KT);

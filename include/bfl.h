@@ -165,6 +165,33 @@ int bfl_count_regions_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t 
 int bfl_count_regions_total_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh,
                                 int64_t* d_counts, int64_t* d_totals);
 
+/* ---- pipelined batch search ------------------------------------------------------------
+ * The loop of scripts/kepler_analysis_script.py:340-455 (oddsratio + thresholder per star) for batches of
+ * light curves on one time base, asynchronous: bfl_pipe_submit enqueues host->device copy, noise estimate,
+ * all hypotheses, region extraction and the device->host copies of ONE batch on the stream of a pipeline
+ * slot and returns; bfl_pipe_wait blocks until that batch's outputs are in host memory.  With depth >= 2
+ * the copies of one batch overlap the kernels of its neighbours (host buffers must be page-locked for that;
+ * pageable buffers work but serialise).  A slot is reused after `depth` submissions: its host outputs must
+ * have been consumed by then.
+ *   noise        how to estimate sigma on device when bfl_pipe_submit gets sk == NULL (copied; may be NULL)
+ *   max_regions  capacity of the region list per batch
+ * bfl_pipe_submit:
+ *   clc  host [B][N]; sk host [B] or NULL
+ *   out_lnO host [B][k1-k0] or NULL (NULL: the log odds never leave the device -- a search needs regions only)
+ *   thresh NaN: no region extraction.  Otherwise contiguous_regions (find.py:15-52) of lnO > thresh per curve:
+ *   out_regions host [max_regions] in arbitrary order (sort by curve, start), out_counts host [B + 3]:
+ *   regions per curve, then {regions in the batch, curves with a region, records produced}
+ *   out_sk host [B] or NULL: the sigmas used.   *job receives the job number for bfl_pipe_wait.           */
+typedef struct bfl_pipe bfl_pipe;
+typedef struct { int32_t curve, start, stop, argmax; double maxval; } bfl_region;
+int bfl_pipe_create(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const bfl_noise_spec* noise, int32_t B, int64_t N,
+                    int64_t k0, int64_t k1, int32_t depth, int32_t max_regions, bfl_pipe** pipe);
+int bfl_pipe_submit(bfl_pipe* pipe, const double* clc, const double* sk, double* out_lnO, double thresh,
+                    bfl_region* out_regions, int64_t* out_counts, double* out_sk, int64_t* job);
+int bfl_pipe_wait(bfl_pipe* pipe, int64_t job, int32_t* nregions);
+int64_t bfl_pipe_launch_count(const bfl_pipe* pipe);
+int bfl_pipe_destroy(bfl_pipe* pipe);
+
 /* ---- injection sweep on device (scripts/flare_detection_efficiency.py:399-651; BASELINE config 5) ----
  * bfl_sweep_simulate_dev: B light curves of N <= 8192 samples, realisation indices first .. first+B-1 (the
  *   stream of a realisation depends on (seed, index) only -- counter-based Philox -- so a sweep sharded over

@@ -15,6 +15,12 @@ reference source is copied into this repository):
 Both are compiled with the reference's own flags (``-O3``, no ``-march``, hence no FMA
 contraction on x86-64) so rounding behaviour is the reference's.
 
+``install_python()`` additionally installs the reference's *Python* package, unmodified, into
+``oracle/_ref/site/bayesflare`` (what ``pip install --target`` would put there; git-ignored like the
+rest of ``oracle/_ref`` but shipped to the GPU box), so that ``bench.py``'s CPU arms can time the
+reference's own NumPy path on the box's host cores.  ``oracle/ref_loader.py`` imports it from there
+(with its in-memory Python-3 patches) when ``/root/reference`` itself is absent.
+
 The recipe is a no-op when ``/root/reference`` is missing (the GPU box): prebuilt files
 travel with the repository snapshot.
 """
@@ -87,5 +93,29 @@ def build(force: bool = False, verbose: bool = False) -> dict:
     return {"liblogmarg": lib, "general": ext}
 
 
+SITE = os.path.join(OUT, "site")
+
+
+def install_python(force: bool = False) -> str | None:
+    """Install the reference's Python package (``*.py`` only, byte for byte) under ``oracle/_ref/site``."""
+    import shutil
+    src = os.path.join(REF_ROOT, "bayesflare")
+    dst = os.path.join(SITE, "bayesflare")
+    if not reference_present():
+        return dst if os.path.isdir(dst) else None
+    if os.path.isdir(dst) and not force:
+        return dst
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    for root, dirs, files in os.walk(src):
+        rel = os.path.relpath(root, src)
+        os.makedirs(os.path.join(dst, rel), exist_ok=True)
+        for f in files:
+            if f.endswith(".py"):
+                shutil.copy2(os.path.join(root, f), os.path.join(dst, rel, f))
+    return dst
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(install_python(force="--force" in sys.argv))

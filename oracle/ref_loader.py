@@ -37,6 +37,11 @@ from . import build_ref
 
 REF_ROOT = build_ref.REF_ROOT
 PKG_DIR = os.path.join(REF_ROOT, "bayesflare")
+if not os.path.isdir(PKG_DIR) and os.path.isdir(os.path.join(build_ref.SITE, "bayesflare")):
+    # the GPU box: /root/reference does not exist there; oracle/build_ref.install_python() put an unmodified
+    # copy of the reference's Python package under oracle/_ref/site (git-ignored, shipped with the snapshot)
+    REF_ROOT = build_ref.SITE
+    PKG_DIR = os.path.join(REF_ROOT, "bayesflare")
 PKG = "bayesflare"
 
 # (module, old, new, expected minimum number of replacements)
@@ -58,7 +63,9 @@ PATCHES = {
 
 
 def available() -> bool:
-    return os.path.isdir(PKG_DIR) and build_ref.reference_present()
+    built = build_ref.build() if build_ref.reference_present() else {"general": None}
+    so = built.get("general") or os.path.join(build_ref.OUT, "general" + build_ref.ext_suffix())
+    return os.path.isdir(PKG_DIR) and os.path.exists(so)
 
 
 def mlab_psd(x, NFFT=None, Fs=2, window=None, noverlap=0, sides="onesided", **_):
