@@ -41,6 +41,7 @@ struct bfl_ctx {
   bool own_stream = false;
   LaunchStats stats;
   bool timing = false;
+  void* counters_zeroed = nullptr;                          // the tile-counter allocation that has been cleared
   cudaStream_t s_in = nullptr, s_out = nullptr;           // copy streams of the pipelined host entry point
   std::vector<cudaEvent_t> pipe_ev;                        // cached events for it
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
@@ -514,7 +515,15 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   if ((rc = c->get("halflogv", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.halflogv = (double*)ptr;
   if ((rc = c->get("uconst", sizeof(double) * (size_t)sv.B, &ptr))) return rc; sc.uconst = (double*)ptr;
   if ((rc = c->get("tile_counters", sizeof(unsigned long long) * (size_t)(sc.NC + 1), &ptr))) return rc;
-  sc.tile_counters = (unsigned long long*)ptr;
+  sc.tile_counters = (unsigned long long*)ptr;      // single-kernel paths: zeroed by k_prep_scalars before every launch
+  // split form: [0] / [1] tile schedulers of the correlation and epilogue kernels, [2] / [3] their exit counters.
+  // Both pairs re-arm themselves at the end of the kernel, so they are cleared once, when allocated.
+  if ((rc = c->get("split_counters", sizeof(unsigned long long) * 4, &ptr))) return rc;
+  if (ptr != c->counters_zeroed) {
+    CK(cudaMemsetAsync(ptr, 0, sizeof(unsigned long long) * 4, c->stream));
+    c->counters_zeroed = ptr;
+  }
+  sc.split_counters = (unsigned long long*)ptr;
   sc.dw = sc.uu = nullptr;
   if (need_general) {
     if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
@@ -565,7 +574,9 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   const bool fused = sv.const_var && !edges && !need_bg && fast_can_fuse(pv, sc, noisepoly);
   if (!fused && (rc = setup_scratch(c, pv, sv, need_general, need_bg, true, sc, wsep))) return rc;
   cudaStream_t s = c->stream;
-  CK(launch_prep(sv, sc, need_general, s, &c->stats));
+  // the split form computes the per-curve scalars inside its correlation kernel and re-arms its own tile
+  // schedulers: no preparation launch
+  if (!(fused && sc.Y)) CK(launch_prep(sv, sc, need_general, s, &c->stats));
   if (fused) {
     std::pair<cudaEvent_t, cudaEvent_t> pr;
     if (c->timing && (rc = timing_begin(c, pr))) return rc;
@@ -966,7 +977,6 @@ int bfl_window_lnB(bfl_ctx* c, bfl_plan* p, int ihyp, const double* clc, const d
 int bfl_count_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n, double thresh, int64_t* d_counts) {
   if (!c || !d_lnO || !d_counts || B < 1 || n < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_count_regions_dev");
   CK(cudaSetDevice(c->device));
-  CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)B, c->stream));
   CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, nullptr, c->stream, &c->stats));
   return BFL_OK;
 }
@@ -1001,7 +1011,6 @@ int bfl_count_regions_total_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int6
   if (!c || !d_lnO || !d_counts || !d_totals || B < 1 || n < 1)
     return fail(BFL_ERR_ARG, "bad argument to bfl_count_regions_total_dev");
   CK(cudaSetDevice(c->device));
-  CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)B, c->stream));
   CK(launch_count_regions(d_lnO, B, n, thresh, d_counts, d_totals, c->stream, &c->stats));
   return BFL_OK;
 }

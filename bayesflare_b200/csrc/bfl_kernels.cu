@@ -384,8 +384,8 @@ __global__ void k_prep_whiten(const double* __restrict__ clc, const double* __re
 }
 
 cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cudaStream_t s, LaunchStats* st) {
-  k_prep_scalars<<<(std::max(sv.B, sc.NC + 1) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
-                                                                   sc.uconst, sc.tile_counters, sc.NC + 1);
+  k_prep_scalars<<<(std::max(sv.B, sc.NC) + 127) / 128, 128, 0, s>>>(sv.sk, sv.cle, sv.seglen, sv.B, sc.sqrtu, sc.halflogv,
+                                                                   sc.uconst, sc.tile_counters, sc.NC);
   st->launches++;
   if (need_general) {
     const int64_t n = sv.seglen * sv.B;
@@ -717,7 +717,10 @@ __global__ void __launch_bounds__(FAST_TPB, BFL_MINBLOCKS) k_window_fast(const F
 //                   phi table, online log-sum-exp per hypothesis, hypotheses combined -> lnO
 // Y makes one round trip through HBM (S * 8 bytes per sample each way), overlapped with the FP64 work.
 struct CorrArgs {
-  const double* data; const double* sqrtu;
+  const double* data;
+  const double* sk; const double* cle;      // per-curve noise sigma, flux errors (constant per curve here) or nullptr
+  double* sqrtu; double* halflogv;          // [B] written for the epilogue (what k_prep_scalars computes)
+  unsigned long long* done_counter;         // warps that have left the tile loop: the last one re-arms both counters
   int64_t seglen, N, seg0, k0, k1;
   int B, tiles_per_curve;
   int64_t total_wtiles;
@@ -747,12 +750,23 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_corr_shapes(const CorrArgs a) {
     long long wt = 0;
     if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
     wt = __shfl_sync(0xffffffffu, wt, 0);
-    if (wt >= a.total_wtiles) break;
+    if (wt >= a.total_wtiles) {
+      // self-resetting scheduler: the last warp of the grid to leave puts both counters back to zero
+      if (lane == 0 && atomicAdd(a.done_counter, 1ULL) == (unsigned long long)gridDim.x * (FAST_TPB / 32) - 1ULL) {
+        *a.tile_counter = 0ULL;
+        *a.done_counter = 0ULL;
+      }
+      break;
+    }
     const int tile = (int)(wt % a.tiles_per_curve);
     const int b = (int)(wt / a.tiles_per_curve);
     const int64_t kbase = a.k0 + (int64_t)tile * TKW;
     {
-      const double su = a.sqrtu[b];
+      // per-curve scalars inline (no separate preparation launch): v = sk^2 + cle^2 as NumPy rounds it (bayes.py:312)
+      const double sg = __ldg(a.sk + b), er = a.cle ? __ldg(a.cle + (size_t)b * a.seglen) : 0.0;
+      const double var = __dadd_rn(__dmul_rn(sg, sg), __dmul_rn(er, er));
+      const double su = sqrt(1.0 / var);
+      if (tile == 0 && lane == 0) { a.sqrtu[b] = su; a.halflogv[b] = 0.5 * log(var); }
       const double* d = a.data + (size_t)b * a.seglen;
       const int64_t lo = a.seg0, hi = min(a.N, a.seg0 + a.seglen);
       __syncwarp();
@@ -789,7 +803,8 @@ struct EpiArgs {
   const double* Y;        // [S][BK]
   const double* halflogv; // [B]
   const double* sqrtu;    // [B]
-  unsigned long long* tile_counter;   // k_epilogue2: next warp tile (zeroed by k_prep_scalars)
+  unsigned long long* tile_counter;   // k_epilogue2: next warp tile (self-resetting)
+  unsigned long long* done_counter;   // k_epilogue2: warps that have left the tile loop
   const unsigned char* plan_block;    // k_epilogue2: per-plan shared-memory block built by k_epilogue2_prepare
   int srows;              // k_epilogue2: rows of the per-thread slice (A shapes of separable + all shapes of dense hypotheses)
   int64_t nk, BK, N, k0;
@@ -1318,7 +1333,13 @@ __global__ void __launch_bounds__(EPI2_TPB, BFL_EPI2_MINB) k_epilogue2(const Epi
     long long wt = 0;
     if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
     wt = __shfl_sync(0xffffffffu, wt, 0);
-    if (wt >= nwt) break;
+    if (wt >= nwt) {
+      if (lane == 0 && atomicAdd(a.done_counter, 1ULL) == (unsigned long long)gridDim.x * (EPI2_TPB / 32) - 1ULL) {
+        *a.tile_counter = 0ULL;      // self-resetting scheduler (see k_corr_shapes)
+        *a.done_counter = 0ULL;
+      }
+      break;
+    }
     int64_t idx = wt * 32 + lane;
     bool valid = idx < a.BK;
     if (!valid) idx = a.BK - 1;
@@ -1484,7 +1505,7 @@ bool fast_split_fits(const PlanView& pv) {
 }
 
 static void fill_epi_plan_args(EpiArgs& a, const PlanView& pv, int noisepoly) {
-  a.Y = nullptr; a.halflogv = nullptr; a.sqrtu = nullptr; a.tile_counter = nullptr; a.plan_block = nullptr;
+  a.Y = nullptr; a.halflogv = nullptr; a.sqrtu = nullptr; a.tile_counter = nullptr; a.done_counter = nullptr; a.plan_block = nullptr;
   a.nk = a.BK = a.N = a.k0 = 0; a.B = 0; a.lnO = nullptr; a.part = nullptr;
   a.G = pv.G; a.nhyp = pv.nhyp; a.H = pv.W / 2;
   for (int h = 0; h <= MAXH; h++) a.hyp_begin[h] = (h <= pv.nhyp) ? pv.hyp_begin[h] : pv.hyp_begin[pv.nhyp];
@@ -1518,9 +1539,9 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   const int64_t nk = sv.k1 - sv.k0;
   const int KT = sc.KT;
   CorrArgs c;
-  c.data = sv.clc; c.sqrtu = sc.sqrtu; c.seglen = sv.seglen; c.N = sv.N; c.seg0 = sv.seg0; c.k0 = sv.k0; c.k1 = sv.k1;
+  c.data = sv.clc; c.sk = sv.sk; c.cle = sv.cle; c.sqrtu = sc.sqrtu; c.halflogv = sc.halflogv; c.seglen = sv.seglen; c.N = sv.N; c.seg0 = sv.seg0; c.k0 = sv.k0; c.k1 = sv.k1;
   c.B = sv.B; c.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
-  c.total_wtiles = (int64_t)c.tiles_per_curve * sv.B; c.tile_counter = sc.tile_counters;
+  c.total_wtiles = (int64_t)c.tiles_per_curve * sv.B; c.tile_counter = sc.split_counters; c.done_counter = sc.split_counters + 2;
   c.shapes = pv.shapes; c.S = pv.S; c.WP = pv.WP; c.Y = sc.Y;
   const size_t smem1 = corr_smem_bytes(pv.S, KT);
   cudaError_t e;
@@ -1544,7 +1565,7 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
 
   EpiArgs a;
   fill_epi_plan_args(a, pv, noisepoly);
-  a.Y = sc.Y; a.halflogv = sc.halflogv; a.sqrtu = sc.sqrtu; a.tile_counter = sc.tile_counters + 1; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
+  a.Y = sc.Y; a.halflogv = sc.halflogv; a.sqrtu = sc.sqrtu; a.tile_counter = sc.split_counters + 1; a.done_counter = sc.split_counters + 3; a.nk = nk; a.BK = (int64_t)sv.B * nk; a.N = sv.N; a.k0 = sv.k0;
   a.B = sv.B; a.lnO = d_lnO; a.part = sc.part;
   constexpr int SPT = BFL_EPI_SPT;
   const size_t smem2 = epi_smem_bytes(pv.G, pv.S, a.arows, SPT);
@@ -3119,25 +3140,36 @@ cudaError_t launch_threshold_edges(const double* d_lnO, int64_t n, double thresh
 }
 
 // number of region starts per curve (a start = above threshold and predecessor not above)
-__global__ void k_count_regions(const double* __restrict__ lnO, int B, int64_t n, double thresh,
-                                unsigned long long* counts, unsigned long long* totals) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * B) return;
-  const int64_t k = i % n;
-  if (!(lnO[i] > thresh)) return;
-  if (k > 0 && lnO[i - 1] > thresh) return;
-  const unsigned long long before = atomicAdd(&counts[i / n], 1ULL);
-  if (totals) {                                   // [0] regions in the batch, [1] curves with at least one
-    atomicAdd(&totals[0], 1ULL);
-    if (before == 0ULL) atomicAdd(&totals[1], 1ULL);
+// one CTA per curve: contiguous_regions (find.py:15-52) counts the samples that OPEN a region
+__global__ void __launch_bounds__(256) k_count_regions(const double* __restrict__ lnO, int B, int64_t n, double thresh,
+                                                       unsigned long long* counts, unsigned long long* totals) {
+  const int b = blockIdx.x;
+  const double* row = lnO + (size_t)b * n;
+  int cnt = 0;
+  for (int64_t k = threadIdx.x; k < n; k += 256) {
+    const bool up = row[k] > thresh;
+    const bool prev = (k > 0) && (row[k - 1] > thresh);
+    cnt += (up && !prev) ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; w++) tot += part[w];
+    counts[b] = (unsigned long long)tot;
+    if (totals && tot > 0) {                      // [0] regions in the batch, [1] curves with at least one
+      atomicAdd(&totals[0], (unsigned long long)tot);
+      atomicAdd(&totals[1], 1ULL);
+    }
   }
 }
 
 cudaError_t launch_count_regions(const double* d_lnO, int B, int64_t n, double thresh, int64_t* d_counts,
                                  int64_t* d_totals, cudaStream_t s, LaunchStats* st) {
-  const int64_t tot = n * B;
-  k_count_regions<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts,
-                                                                (unsigned long long*)d_totals);
+  k_count_regions<<<(unsigned)B, 256, 0, s>>>(d_lnO, B, n, thresh, (unsigned long long*)d_counts,
+                                              (unsigned long long*)d_totals);
   st->launches++;
   return cudaGetLastError();
 }

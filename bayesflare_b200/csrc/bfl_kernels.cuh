@@ -80,6 +80,7 @@ struct Scratch {
   double2* part;   // [nhyp][NC][B*nk] partial log-sum-exp (max, sum)
   double* bgabs;   // [B*nk] polynomial-only log Bayes factor (no sumlogsigma) or nullptr
   unsigned long long* tile_counters;  // [NC] dynamic tile scheduler state
+  unsigned long long* split_counters; // [4] split form: self-resetting tile schedulers + exit counters
   double* Y;       // [S][B*nk] shape correlations (split form) or nullptr
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk

@@ -346,19 +346,24 @@ def run_ours(args, rank, local_rank, world):
 
     peak_tf, _ = _lib.fp64_peak(ctxs[0], 4096)    # roofline denominator, measured live (burst)
 
+    # rank 0's samples are the ones reported; the other ranks sample sparsely (NVML calls of 8 processes
+    # serialise in the driver)
+    sampler = ClockSampler(physical_gpu_index(local_rank), period=0.002 if rank == 0 else 0.05)
+    sampler.start()
+    align = torch.zeros(1, dtype=torch.int64, device=dev)
     for i in range(args.warmup):
         step(i, row=1)
     drain()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # rank 0's samples are the ones reported; the other ranks sample sparsely (NVML calls hold the GIL and
-    # would otherwise compete with the launch loop on a box running 8 ranks)
-    sampler = ClockSampler(physical_gpu_index(local_rank), period=0.002 if rank == 0 else 0.025)
-    sampler.start()
     d_tot[0].zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        # Host threads leave the barrier up to milliseconds apart (8 Python processes on one box); a 20-step
+        # region is only ~4 ms long and ends in a collective that waits for the last rank.  So the ranks are
+        # aligned once more ON THE DEVICE: an all-reduce enqueued right in front of the start event -- every
+        # rank's region starts when the last rank's GPU gets there, with the K steps already queued behind it.
+        dist.all_reduce(align)
     e0.record(streams[0])
     fork_streams()
     for i in range(args.steps):
