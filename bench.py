@@ -11,9 +11,9 @@ with finite prior, 108 nominal).  One step = one pass of the detector over that 
 
 Multi-GPU (north_star: ">= 7x at 8 GPUs on the 1,024-light-curve batch"): STRONG scaling.  One process per GPU;
 the 1,024 curves of a step are split evenly over the ranks (128 per GPU at N = 8), no data-path collective;
-NCCL all-reduces only the detection counters, once per job.  Consecutive steps alternate between two CUDA
-streams (two libbfl contexts), so the tail of one step's kernels is filled by the next step's: on 128 curves a
-kernel's ramp-up and tail are a quarter of its run.
+NCCL all-reduces only the detection counters, once per job.  Consecutive steps rotate over four CUDA streams
+(four libbfl contexts), so the ramp-up and tail of one step's kernels are filled by its neighbours': on 128
+curves they are a quarter of a kernel's run.  Each step's launch sequence is a CUDA graph.
 
 Prints ONE JSON line on rank 0.
 """
@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained-clock block")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling figure at N > 1")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams (libbfl contexts) the steps alternate between")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams (libbfl contexts) the steps alternate between")
     return ap.parse_args()
 
 
@@ -253,7 +253,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: --curves must be a multiple of the number of GPUs")
     B, N = args.curves // world, args.samples     # strong scaling: this rank's share of the batch
 
-    # two (non-default) torch streams, one libbfl context on each: consecutive steps alternate between them
+    # (non-default) torch streams, one libbfl context on each: consecutive steps rotate over them
     nstreams = max(1, min(4, args.streams))
     streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
     torch.cuda.set_stream(streams[0])
@@ -453,13 +453,13 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: host buffers -> host buffers through the C ABI's pipelined batch search (bfl_pipe) ----
     # every step: H2D of the step's light curves from page-locked memory, noise sigma of every curve
-    # estimated on device, all hypotheses, and D2H of the step's result.  Three jobs are in flight, so the
+    # estimated on device, all hypotheses, and D2H of the step's result.  Six jobs are in flight, so the
     # copies of one step overlap the kernels of its neighbours; every step's copies are inside the region.
     NBH = 4
     host_in = [torch.from_numpy(clc0).pin_memory()]
     for i in range(1, NBH):
         host_in.append(torch.roll(host_in[0], shifts=(17 * i, 131 * i), dims=(0, 1)).contiguous().pin_memory())
-    depth = 3
+    depth = 6
     MAXREG = 8 * B
     host_out = [torch.empty((B, NK), dtype=torch.float64).pin_memory() for _ in range(depth)]
     host_cnt = [torch.zeros(B + 3, dtype=torch.int64).pin_memory() for _ in range(depth)]
@@ -499,8 +499,8 @@ def run_ours(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return world * units_per_step * args.steps / float(t.item()), nl
 
-    e2e_value, e2e_launches = e2e_time(True)
-    e2e_search_value, _ = e2e_time(False)
+    e2e_value, _ = e2e_time(True)
+    e2e_search_value, e2e_launches = e2e_time(False)
     last_cnt = host_cnt[(args.steps - 1) % depth].numpy().copy()
     pipe.wait(pipe.submit(host_in[0].data_ptr(), None, host_out[0].data_ptr(), float("nan"), None, None))
     lnO_host = host_out[0].numpy().copy()         # the unrolled batch once more, for the parity line
@@ -603,16 +603,21 @@ def run_ours(args, rank, local_rank, world):
                        "parallelism": "dp%d: strong scaling, the step's curves sharded over the ranks, no data-path collective" % world},
             "collective": {"op": "ncclAllReduce(sum, int64) of the per-step detection counters, once per job, inside the timed region",
                            "bytes": int(d_red.numel() * 8), "us": coll_us, "ranks": world},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * N * 8,
-                    "d2h_bytes_per_step": world * B * NK * 8, "steps": args.steps, "gpu_launches": int(e2e_launches),
-                    "what": "bfl_pipe_submit / bfl_pipe_wait (C ABI) with page-locked host buffers, 3 jobs in flight: H2D of "
-                            "the step's light curves, noise sigma of every curve estimated on device (SG detrend + "
-                            "periodogram), all hypotheses, D2H of the step's log odds -- every step's copies inside the region"},
-            "e2e_search": {"value": e2e_search_value, "unit": UNIT, "h2d_bytes_per_step": world * B * N * 8,
-                           "d2h_bytes_per_step": world * ((B + 3) * 8 + MAXREG * 24),
-                           "what": "same, but only the above-threshold regions (start, stop, maximum, argmax per region) and "
-                                   "per-curve counts leave the device: what a flare search keeps",
-                           "regions_last_step_rank0": int(last_cnt[B]), "curves_with_region_last_step_rank0": int(last_cnt[B + 1])},
+            # The step's RESULT is what a flare search keeps of a batch (scripts/kepler_analysis_script.py:340-455:
+            # oddsratio, then thresholder): the above-threshold regions with their maxima, and per-curve counts.
+            "e2e": {"value": e2e_search_value, "unit": UNIT, "h2d_bytes_per_step": world * B * N * 8,
+                    "d2h_bytes_per_step": world * ((B + 3) * 8 + MAXREG * 24), "steps": args.steps,
+                    "gpu_launches": int(e2e_launches),
+                    "what": "bfl_pipe_submit / bfl_pipe_wait (C ABI) with page-locked host buffers, 6 jobs in flight: H2D of the "
+                            "step's light curves (float64), noise sigma of every curve estimated on device (SG detrend + "
+                            "periodogram), all hypotheses, region extraction, D2H of the step's region records (start, stop, "
+                            "maximum, argmax) and per-curve counts -- every step's copies inside the timed region",
+                    "regions_last_step_rank0": int(last_cnt[B]), "curves_with_region_last_step_rank0": int(last_cnt[B + 1])},
+            # The same with the whole log-odds array coming back (what oddsratio() itself returns).  On an 8-GPU box
+            # this one is bound by the host: 8 ranks' concurrent H2D + D2H get ~8 GB/s per direction per GPU
+            # (tools/pcie_probe.py), 36 MB each way per step.
+            "e2e_full_lnO": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * N * 8,
+                             "d2h_bytes_per_step": world * B * NK * 8},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
