@@ -231,59 +231,55 @@ class ParameterEstimationGrid:
         self.prior = self.model.prior
 
     def set_grid(self, ranges={}):
-        """bayes.py:771-816.  As in the reference, single values are stored as float32."""
-        if len(ranges) == 0:
+        """Grid axes from a dictionary of ranges (bayes.py:771-816): ``(lo, hi, n)`` -> ``np.linspace``, a single
+        value -> a one-point axis, which the reference stores as float32 -- kept, it changes the value."""
+        if not ranges:
             print("Must specify a dictionary of ranges")
             return
-        if len(self.model.ranges) == 0:
+        if not self.model.ranges:
             self.model.set_params(ranges)
+        missing = [p for p in self.paramNames if p not in ranges]
+        if missing:
+            print("Error. The parameter %s is not in the dictionary" % missing[0])
+            return
         for p in self.paramNames:
-            if p not in ranges:
-                print("Error. The parameter %s is not in the dictionary" % p)
-                return
-            irange = ranges[p]
-            if not isinstance(irange, tuple):
-                irange = (irange,)
-            if len(irange) == 3:
-                if irange[0] < irange[1] and irange[2] > 1:
-                    vals = np.linspace(irange[0], irange[1], int(irange[2]))
-                else:
+            spec = ranges[p] if isinstance(ranges[p], tuple) else (ranges[p],)
+            if len(spec) == 1:
+                self.paramValues[p] = np.array(spec, dtype='float32')
+            elif len(spec) == 3:
+                lo, hi, n = spec
+                if not (lo < hi and n > 1):
                     print("%s range has an upper bound smaller than the lower bound! Try again." % p)
                     return
-            elif len(irange) == 1:
-                vals = np.array([irange[0]], dtype='float32')
-            self.paramValues[p] = vals
+                self.paramValues[p] = np.linspace(lo, hi, int(n))
 
     def lightcurve_chunk(self, centidx, length):
-        """bayes.py:818-846"""
-        ll = len(self.lightcurve.cts)
-        dl = int(length / 2)
-        startidx = max(centidx - dl, 0)
-        endidx = centidx + dl + 1
-        if endidx > ll - 1:
-            endidx = ll
+        """Cut the light curve down to ``length`` samples centred on ``centidx`` (bayes.py:818-846): the window is
+        [centidx - length//2, centidx + length//2], clipped to the series (a stop on the last sample moves to the end)."""
         lc = self.lightcurve
-        lc.cts, lc.clc, lc.cle = lc.cts[startidx:endidx], lc.clc[startidx:endidx], lc.cle[startidx:endidx]
+        n = len(lc.cts)
+        half = int(length / 2)
+        stop = centidx + half + 1
+        sel = slice(max(centidx - half, 0), n if stop > n - 1 else stop)
+        lc.cts, lc.clc, lc.cle = lc.cts[sel], lc.clc[sel], lc.cle[sel]
 
     def lightcurve_dynamic_range(self):
         return (np.amin(self.lightcurve.clc), np.amax(self.lightcurve.clc))
 
     def set_sigma(self, lightcurve, detrend=True, dtlen=55, dtorder=4, noiseestmethod='powerspectrum', estfrac=0.5,
                   tvsigma=1.0):
-        """bayes.py:862-910"""
-        tmpcurve = copy(lightcurve)
+        """Noise sigma of the (optionally Savitzky-Golay detrended) curve (bayes.py:862-910)."""
+        work = copy(lightcurve)
         if detrend:
-            tmpcurve.detrend(method='savitzkygolay', nbins=dtlen, order=dtorder)
-        if noiseestmethod == 'powerspectrum':
-            sigma = estimate_noise_ps(tmpcurve, estfrac=estfrac)[0]
-        elif noiseestmethod == 'tailveto':
-            sigma = estimate_noise_tv(tmpcurve.clc, sigma=tvsigma)[0]
-        elif noiseestmethod == 'std':
-            sigma = np.std(tmpcurve.clc)
-        else:
+            work.detrend(method='savitzkygolay', nbins=dtlen, order=dtorder)
+        estimators = {'powerspectrum': lambda: estimate_noise_ps(work, estfrac=estfrac)[0],
+                      'tailveto': lambda: estimate_noise_tv(work.clc, sigma=tvsigma)[0],
+                      'std': lambda: np.std(work.clc)}
+        if noiseestmethod not in estimators:
             print("Noise estimation method must be 'powerspectrum' or 'tailveto'")
-            sigma = None
-        self.noiseSigma = sigma
+            self.noiseSigma = None
+            return
+        self.noiseSigma = estimators[noiseestmethod]()
 
     def calculate_posterior(self, paramValues=None, lightcurve=None, sigma=None, margbackground=True, bgorder=4,
                             ncpus=None):
@@ -326,102 +322,89 @@ class ParameterEstimationGrid:
                             params, logprior, bgorder + 1, polyms, sk, margbackground, sg=sg)
         self.posterior = post.reshape(tuple(sp))
 
-    # ---- post-processing (host; bayes.py:1057-1301) ---------------------------------------
+    # ---- post-processing (bayes.py:1057-1301): marginals by log-trapezium integration on the device ----
+    def _axis(self, name):
+        return np.asarray(self.paramValues[name], dtype=float)
+
+    def _integrate_out(self, drop):
+        """Log posterior with the axes named in ``drop`` integrated out (``bfl_logtrapz``, one launch per axis, in
+        the order of ``paramNames`` as the reference does); one-point axes are simply removed (bayes.py:1098-1101).
+        Returns the array and the names of the axes it still has."""
+        ctx = _lib.default_context()
+        logp, names = np.asarray(self.posterior, dtype=float), list(self.paramNames)
+        for name in [p for p in self.paramNames if p in drop]:
+            ax = names.index(name)
+            if logp.shape[ax] == 1:
+                logp = np.take(logp, 0, axis=ax)
+            else:
+                logp = _lib.logtrapz_axis0(ctx, np.ascontiguousarray(np.moveaxis(logp, ax, 0)), self._axis(name))
+            del names[ax]
+        return logp, names
+
     def marginalised_posterior(self, parameter=None):
+        """Normalised posterior of one parameter (bayes.py:1057-1124)."""
         if parameter not in self.paramNames:
             print("Given parameter (%s) is not in model" % parameter)
             return None
         if self.posterior is None:
             print("Posterior not yet defined!")
             return None
-        idx = 0
-        shortpars = []
-        for i, p in enumerate(self.paramNames):
-            if parameter.lower() == p:
-                idx = i
-            else:
-                shortpars.append(p)
-        nump = len(self.paramNames)
-        pv = self.paramValues
-        margp = np.copy(self.posterior)
-        if idx < nump - 1:
-            margp = np.rollaxis(margp, idx, nump)
-        for p in shortpars:
-            if margp.shape[0] == 1:
-                margp = margp[0]
-            else:
-                margp = np.apply_along_axis(logtrapz, 0, margp, np.asarray(pv[p], dtype=float))
-        if len(margp) > 1:
-            area = logtrapz(margp, np.asarray(pv[parameter.lower()], dtype=float))
-        else:
-            area = 1.
-        margp = np.exp(margp - area)
-        self.margposteriors[parameter.lower()] = np.copy(margp)
-        return margp
+        name = parameter.lower()
+        logp, _ = self._integrate_out([p for p in self.paramNames if p != name])
+        logp = np.atleast_1d(logp)
+        # a one-point axis is "normalised" by the constant 1, as the reference does (bayes.py:1117-1120)
+        lognorm = logtrapz(logp, self._axis(name)) if logp.size > 1 else 1.
+        self.margposteriors[name] = np.exp(logp - lognorm)
+        return np.copy(self.margposteriors[name])
 
     def marginalise_all(self):
         for p in self.paramNames:
             self.marginalised_posterior(p)
 
     def marginalised_posterior_2D(self, parameters=None):
+        """Normalised joint posterior of two parameters, indexed [parameters[0], parameters[1]] (bayes.py:1135-1210)."""
         if not isinstance(parameters, list) or len(parameters) != 2:
             print("Must supply a list of two parameters")
             return None
-        for p in parameters:
-            if p.lower() not in self.paramNames:
-                print("Given parameter (%s) is not in model" % p)
+        pair = [p.lower() for p in parameters]
+        for given, p in zip(parameters, pair):
+            if p not in self.paramNames:
+                print("Given parameter (%s) is not in model" % given)
                 return None
         if self.posterior is None:
             print("Posterior not yet defined!")
             return None
-        nump = len(self.paramNames)
-        pv = self.paramValues
-        if nump < 3:
+        if len(self.paramNames) < 3:
             print("No need to marginalise, posterior is already 2d or 1d")
             return None
-        idx1 = idx2 = 0
-        shortpars = []
-        for i, p in enumerate(self.paramNames):
-            if parameters[0].lower() == p:
-                idx1 = i
-            elif parameters[1].lower() == p:
-                idx2 = i
-            else:
-                shortpars.append(p)
-        margp = np.copy(self.posterior)
-        if idx2 < nump - 1:
-            margp = np.rollaxis(margp, idx2, nump)
-            if idx2 < idx1:
-                idx1 = idx1 - 1
-        if idx1 < nump - 2:
-            margp = np.rollaxis(margp, idx1, nump - 1)
-        for p in shortpars:
-            if margp.shape[0] == 1:
-                margp = margp[0]
-            else:
-                margp = np.apply_along_axis(logtrapz, 0, margp, np.asarray(pv[p], dtype=float))
-        area = np.apply_along_axis(logtrapz, 0, np.copy(margp), np.asarray(pv[parameters[0].lower()], dtype=float))
-        area = logtrapz(area, np.asarray(pv[parameters[1].lower()], dtype=float))
-        return np.exp(margp - area)
+        logp, left = self._integrate_out([p for p in self.paramNames if p not in pair])
+        if left != pair:
+            logp = logp.T
+        ctx = _lib.default_context()
+        lognorm = logtrapz(_lib.logtrapz_axis0(ctx, np.ascontiguousarray(logp), self._axis(pair[0])), self._axis(pair[1]))
+        return np.exp(logp - lognorm)
 
     def maximum_posterior(self):
+        """Largest grid value of the log posterior and the parameters there (bayes.py:1212-1236)."""
         if self.posterior is None:
             print("Posterior not defined")
             return None
-        q = np.unravel_index(self.posterior.argmax(), self.posterior.shape)
-        self.maxposterior = self.posterior[q]
-        for j, p in enumerate(self.paramNames):
-            self.maxpostparams[p] = self.paramValues[p][q[j]]
+        at = np.unravel_index(int(np.argmax(self.posterior)), self.posterior.shape)
+        self.maxposterior = self.posterior[at]
+        self.maxpostparams.update({p: self.paramValues[p][i] for p, i in zip(self.paramNames, at)})
         return self.maxposterior, self.maxpostparams
 
-    def maximum_posterior_snr(self):
+    def _best_fit_curve(self):
         if self.maxposterior is None:
             self.maximum_posterior()
-        m = self.model.model(self.maxpostparams, ts=self.lightcurve.cts)
-        return np.sqrt(np.sum(m ** 2)) / self.noiseSigma
+        return self.model.model(self.maxpostparams, ts=self.lightcurve.cts)
+
+    def maximum_posterior_snr(self):
+        """Optimal signal-to-noise ratio of the maximum-posterior model (bayes.py:1238-1266)."""
+        return np.sqrt(np.sum(self._best_fit_curve() ** 2)) / self.noiseSigma
 
     def maximum_posterior_ew(self):
-        if self.maxposterior is None:
-            self.maximum_posterior()
-        m = self.model.model(self.maxpostparams, ts=self.lightcurve.cts)
-        return getattr(np, 'trapezoid', getattr(np, 'trapz', None))(m, self.lightcurve.cts) / np.median(self.lightcurve.clc - m + self.lightcurve.dc)
+        """Equivalent width of the maximum-posterior model (bayes.py:1268-1301)."""
+        best = self._best_fit_curve()
+        trapezoid = getattr(np, 'trapezoid', None) or np.trapz
+        return trapezoid(best, self.lightcurve.cts) / np.median(self.lightcurve.clc - best + self.lightcurve.dc)

@@ -269,6 +269,8 @@ def gold_pe(bf):
             out["ref_maxpost"] = np.array(mp)
             out["ref_maxpost_params"] = np.array([mpar[p] for p in ("t0", "tauexp", "taugauss", "amp")], dtype=float)
             out["ref_snr"] = np.array(pe.maximum_posterior_snr())
+            out["ref_marg2d_taugauss_tauexp"] = pe.marginalised_posterior_2D(["taugauss", "tauexp"])
+            out["ref_marg2d_amp_taugauss"] = pe.marginalised_posterior_2D(["amp", "taugauss"])
     pe = bf.ParameterEstimationGrid("flare", lc)
     pe.lightcurve_chunk(idxt0, 55)
     pe.set_grid(ranges={"taugauss": (0., 3600., 6), "tauexp": (0., 12000., 5), "amp": amprange, "t0": (t0,)})
@@ -286,6 +288,74 @@ def gold_pe(bf):
     out["ref_post_sg21_o2"] = pe.posterior
     out["ref_sg_chunk_clc"] = pe.lightcurve.clc.copy()
     save("pegrid", **out)
+
+
+def _force_sk_detector(sk):
+    """Make the reference's noise estimators return a given sigma (so that the golden does not depend on the
+    un-pinned mlab.psd shim): bayes.py:235-246 calls estimate_noise_ps / estimate_noise_tv by module name."""
+    import bayesflare.stats.bayes as rb
+    rb.estimate_noise_ps = lambda lc, estfrac=0.5: (sk, sk)
+    rb.estimate_noise_tv = lambda d, sigma=1.0: (sk, 0.0)
+
+
+def gold_trend(bf):
+    """Data whose polynomial-like component is hundreds of sigma high -- the regime where the reference's own
+    elimination of raw monomials loses digits (hard part 1).  The fixtures are
+    the outputs of the REFERENCE ITSELF (np.correlate and all), so a test can tell the reference's rounding noise
+    from an error of ours: (a) slow sinusoidal trend 400 sigma high, (b) sigma = 50 on a DC offset of 3000."""
+    out = {}
+    rng = np.random.RandomState(911)
+    N = 1100
+    ts = np.arange(N) * DT_LONG
+    base = rng.randn(N) + ref_flare(bf, ts, ts[500], 9., 1500., 3500.)
+    a = base + 400.0 * np.sin(2 * np.pi * ts / (6.3 * 86400.))
+    N2 = 600
+    b = 50.0 * rng.randn(N2) + 3000.0 + ref_flare(bf, ts[:N2], ts[300], 400., 1500., 3500.)
+    import importlib
+    rb = importlib.import_module("bayesflare.stats.bayes")
+    keep = (rb.estimate_noise_ps, rb.estimate_noise_tv)
+    try:
+        for name, clc, sk in (("a", a, 1.0), ("b", b, 50.0)):
+            _force_sk_detector(sk)
+            lc = ref_loader.RefLightcurve(ts[:len(clc)], clc)
+            det = bf.OddsRatioDetector(lc)
+            lnO, _ = det.oddsratio()
+            out[name + "_cts"], out[name + "_clc"], out[name + "_sk"] = ts[:len(clc)], clc, np.array(sk)
+            out["ref_" + name + "_lnO"] = np.array(lnO)
+    finally:
+        rb.estimate_noise_ps, rb.estimate_noise_tv = keep
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        np.show_config()
+    out["numpy_config"] = np.array(buf.getvalue()[:4000])
+    save("trend", **out)
+
+
+def gold_transit5(bf):
+    """BASELINE config 5's transit-model odds at the sweep's shape: N = 1639 (tlength 2893536 s,
+    scripts/flare_detection_efficiency.py:210-216), sinusoidal variation, one injected transit
+    (:291-312, 444-453), Bayes(lc, Transit).bayes_factors_marg_poly_bgd with the scripts' settings (bglen 55,
+    bgorder 4, tail-veto noise).  Transit.prior is executable only with the two undefined names fixed
+    (oracle/ref_loader.py PATCHES)."""
+    rng = np.random.RandomState(515)
+    N = int(np.ceil(2893536. / DT_LONG))
+    ts = np.arange(N) * DT_LONG
+    clc = rng.randn(N) + 2.5 * np.sin(2 * np.pi * ts / (9.1 * 86400.) + 1.1)
+    tr = bf.Transit(ts, amp=1.)
+    clc = clc + tr.model({"t0": ts[700], "amp": 6.0, "sigmag": 2400., "tauf": 7000.})
+    clc = clc - np.median(clc)
+    lc = ref_loader.RefLightcurve(ts, clc)
+    ranges = {"t0": (np.inf,), "sigmag": (1800., 10800., 4), "tauf": (1800., 14400., 5), "amp": (1.,)}
+    B = bf.Bayes(lc, bf.Transit(ts, amp=1, paramranges=ranges))
+    B.bayes_factors_marg_poly_bgd(bglen=55, bgorder=4, noiseestmethod="tailveto", tvsigma=1.0, halfrange=True)
+    from copy import deepcopy
+    tmp = deepcopy(lc)
+    tmp.detrend(method="savitzkygolay", nbins=55, order=4)
+    sk = bf.estimate_noise_tv(tmp.clc, sigma=1.0)[0]
+    M = B.marginalise_full()
+    save("transit5", cts=ts, clc=clc, ref_sk=np.array(sk), ref_lnB=B.lnBmargAmp, ref_marg=M.lnBmargAmp,
+         sigmag=np.array(ranges["sigmag"]), tauf=np.array(ranges["tauf"]))
 
 
 def gold_ingest(bf):
@@ -332,7 +402,12 @@ def gold_ingest(bf):
 
 def main():
     bf = ref_loader.load_reference()
-    which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid", "ingest"]
+    which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid", "ingest",
+                             "trend", "transit5"]
+    if "trend" in which:
+        gold_trend(bf)
+    if "transit5" in which:
+        gold_transit5(bf)
     if "ingest" in which:
         gold_ingest(bf)
     if "scalars" in which:
