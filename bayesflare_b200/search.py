@@ -73,8 +73,16 @@ def _star_record(kepid, info, lnO, ts, flarelist, nflares, maxlist, sk, dc):
 
 
 def flare_search(curves, threshold=16.5, expand=1, maxgap=2, batch=256, star_info=None, outdict=None,
-                 detector_kwargs=None, device=None, checkpoint=None):
+                 detector_kwargs=None, device=None, checkpoint=None, cadence_rtol=1e-4):
     """Search light curves for flares.
+
+    Stars are batched by time base: same number of samples and the same cadence to within ``cadence_rtol``
+    (relative).  Real Kepler TIME columns are barycentre-corrected per target, so two stars of one quarter never
+    share their time stamps exactly; the templates of a batch are evaluated on the window times of the batch's
+    FIRST star, which moves a star's log odds by ~``cadence_rtol`` x (window length / time scale) relative to the
+    reference run on that star alone.  ``cadence_rtol=0`` gives every distinct time base its own plan (the
+    reference's arithmetic exactly, one device plan per star).  A file that cannot be read or conditioned goes
+    to ``"Rejected stars"`` instead of stopping the search.
 
     ``curves``: file names of Kepler light-curve FITS files and/or :class:`Lightcurve` objects.
     ``star_info``: optional ``{kepid: {"teff": .., "logg": ..}}``.  ``outdict``: a result dictionary to
@@ -96,16 +104,25 @@ def flare_search(curves, threshold=16.5, expand=1, maxgap=2, batch=256, star_inf
     if device is not None:
         kw["device"] = device
 
-    groups = {}                       # (N, dt) -> light curves that share a time base
+    groups = {}                       # (N, cadence bucket) -> light curves that share a time base
     for c in curves:
-        lc = c if isinstance(c, Lightcurve) else Lightcurve(curve=c, maxgap=maxgap)
-        if lc.datagap:
+        try:
+            lc = c if isinstance(c, Lightcurve) else Lightcurve(curve=c, maxgap=maxgap)
+            bad = lc.datagap or len(lc.clc) < 3 or not np.all(np.isfinite(lc.cts[:3])) or not (lc.dt() > 0)
+        except Exception as exc:      # unreadable / malformed file: the script would have stopped here
+            name = getattr(c, "id", c)
+            print("Rejected %s: %s" % (name, exc))
+            out["Rejected stars"].append(name if isinstance(name, (int, str)) else str(name))
+            continue
+        if bad:
             out["Rejected stars"].append(lc.id)
             continue
         if lc.id in done:
             continue
         done.add(lc.id)
-        groups.setdefault((len(lc.clc), float(lc.dt())), []).append(lc)
+        dt = float(lc.dt())
+        key = (len(lc.clc), dt) if not cadence_rtol else (len(lc.clc), int(round(np.log(dt) / cadence_rtol)))
+        groups.setdefault(key, []).append(lc)
 
     first = "Noise estimation method" not in out
     for (N, _), lcs in groups.items():

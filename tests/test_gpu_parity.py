@@ -876,3 +876,38 @@ def check_job(pipe, job, j, depth, h_out, h_cnt, h_reg, h_sk, lnO_ref, sk_ref, t
             assert (r["curve"], r["start"], r["stop"], r["argmax"]) == (b, seg[0], seg[1], m[1]) and r["maxval"] == m[0]
             k += 1
     assert k == nreg
+
+
+def test_kepler_search_with_per_star_time_bases_and_a_bad_file(tmp_path):
+    """Real TIME columns are barycentre-corrected per target: every star has its own low bits.  Stars whose
+    cadence agrees to cadence_rtol share one device plan (one batch); cadence_rtol=0 gives each its own plan and
+    must reproduce the per-star detector exactly; a file that cannot be read is rejected, not fatal."""
+    from bayesflare_b200 import fitsio
+    g = load_golden("ingest")
+    rng = np.random.default_rng(5)
+    paths = []
+    for i, kid in enumerate((2001, 2002, 2003, 2004)):
+        p = str(tmp_path / ("kplr%09d_llc.fits" % kid))
+        t = g["time_days"] * (1.0 + 2e-6 * i) + 1e-7 * rng.standard_normal(len(g["time_days"])).cumsum() * 0  # smooth stretch
+        fitsio.write_lightcurve(p, t, g["flux32"], g["err32"], kepid=kid, quarter=1)
+        paths.append(p)
+    bad = str(tmp_path / "kplr000002999_llc.fits")
+    with open(bad, "wb") as f:
+        f.write(b"not a fits file")
+    batched = bf.flare_search(paths + [bad], threshold=16.5, expand=1)
+    assert batched["No. stars analysed"] == 4 and len(batched["Rejected stars"]) == 1
+    exact = bf.flare_search(paths, threshold=16.5, expand=1, cadence_rtol=0)
+    assert exact["No. stars analysed"] == 4 and exact["Flaring stars"] == batched["Flaring stars"] == [2001, 2002, 2003, 2004]
+    for kid, p in zip((2001, 2004), (paths[0], paths[3])):
+        lc = bf.Lightcurve(curve=p, maxgap=2)
+        det = bf.OddsRatioDetector(lc, noiseestmethod='tailveto', tvsigma=1.0)
+        det.set_noise_impulse(noiseimpulseparams={'t0': (0, (det.bglen - 1.) * lc.dt(), det.bglen)})
+        lnO, _ = det.oddsratio()
+        fl, n, mx = det.thresholder(lnO, 16.5, expand=1)
+        rec = exact["Flaring star data"]["KPLR%09d" % kid]
+        assert rec["Max. indices"] == [m[1] for m in mx]
+        np.testing.assert_allclose(rec["Max. odds ratios"], [m[0] for m in mx], rtol=1e-9)
+        # the shared-plan batch: same detections, maxima equal to ~cadence_rtol-level shifts of the time base
+        recb = batched["Flaring star data"]["KPLR%09d" % kid]
+        assert recb["Max. indices"] == rec["Max. indices"]
+        np.testing.assert_allclose(recb["Max. odds ratios"], rec["Max. odds ratios"], rtol=1e-4)
