@@ -81,6 +81,8 @@ SIGNATURES = {
                                               C.c_void_p]),
     "bfl_sweep_simulate_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
+    "bfl_sweep_inject_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "bfl_sweep_score_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_double,
                                       C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bfl_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(Hypothesis), C.c_int,
@@ -97,6 +99,8 @@ SIGNATURES = {
     "bfl_detector_odds_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_void_p]),
+    "bfl_batch_regions_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_int32,
+                                        C.c_void_p]),
     "bfl_pipe_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(NoiseSpec), C.c_int32, C.c_int64, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "bfl_pipe_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
@@ -176,7 +180,11 @@ class Context:
         """Simulate a batch of light curves on the device (device addresses; see ``bfl_sweep_simulate_dev``)."""
         check(self.lib.bfl_sweep_simulate_dev(self.handle, int(seed), int(first), int(B), int(N), int(halfwin), float(dt),
                                               float(nstd), float(sinusoid_amp), float(snr_lo), float(snr_hi),
-                                              1 if inject else 0, d_clc, d_truth))
+                                              int(inject), d_clc, d_truth))
+
+    def sweep_inject_dev(self, kind, B, N, dt, d_sk, d_truth, d_clc):
+        """Add the recorded injections (kind 1 flare, 2 transit) rescaled with the per-curve sigma ``d_sk``."""
+        check(self.lib.bfl_sweep_inject_dev(self.handle, int(kind), int(B), int(N), float(dt), d_sk, d_truth, d_clc))
 
     def sweep_score_dev(self, d_lnO, B, nk, halfwin, d_truth, thresh, nbins, snr_max, d_injected, d_detected, d_counters):
         """Match detections to injections and accumulate the efficiency histograms (``bfl_sweep_score_dev``)."""
@@ -195,6 +203,11 @@ class Context:
         else:
             check(self.lib.bfl_count_regions_total_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_counts,
                                                        d_totals))
+
+    def batch_regions_dev(self, d_lnO, B, n, thresh, d_regions, max_regions, d_counts):
+        """Above-threshold regions of a device-resident batch (device addresses; ``bfl_batch_regions_dev``)."""
+        check(self.lib.bfl_batch_regions_dev(self.handle, d_lnO, int(B), int(n), float(thresh), d_regions, int(max_regions),
+                                             d_counts))
 
     def close(self):
         if getattr(self, "handle", None):

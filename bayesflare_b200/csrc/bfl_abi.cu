@@ -981,6 +981,16 @@ int bfl_count_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n,
   return BFL_OK;
 }
 
+int bfl_batch_regions_dev(bfl_ctx* c, const double* d_lnO, int32_t B, int64_t n, double thresh, bfl_region* d_regions,
+                          int32_t max_regions, int64_t* d_counts) {
+  if (!c || !d_lnO || !d_regions || !d_counts || B < 1 || n < 1 || max_regions < 1)
+    return fail(BFL_ERR_ARG, "bad argument to bfl_batch_regions_dev");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)(B + 3), c->stream));
+  CK(launch_batch_regions(d_lnO, B, n, thresh, (RegionRec*)d_regions, max_regions, d_counts, d_counts + B, c->stream, &c->stats));
+  return BFL_OK;
+}
+
 int bfl_sweep_simulate_dev(bfl_ctx* c, uint64_t seed, int64_t first, int32_t B, int32_t N, int32_t halfwin, double dt,
                            double nstd, double sinusoid_amp, double snr_lo, double snr_hi, int32_t inject, double* d_clc,
                            double* d_truth) {
@@ -991,6 +1001,15 @@ int bfl_sweep_simulate_dev(bfl_ctx* c, uint64_t seed, int64_t first, int32_t B, 
   CK(cudaSetDevice(c->device));
   CK(launch_sweep_simulate(seed, first, B, N, halfwin, dt, nstd, sinusoid_amp, snr_lo, snr_hi, inject, d_clc, d_truth,
                            c->stream, &c->stats));
+  return BFL_OK;
+}
+
+int bfl_sweep_inject_dev(bfl_ctx* c, int32_t kind, int32_t B, int32_t N, double dt, const double* d_sk,
+                         const double* d_truth, double* d_clc) {
+  if (!c || !d_sk || !d_truth || !d_clc) return fail(BFL_ERR_ARG, "null argument to bfl_sweep_inject_dev");
+  if ((kind != 1 && kind != 2) || B < 1 || N < 2 || !(dt > 0.0)) return fail(BFL_ERR_ARG, "bad argument to bfl_sweep_inject_dev");
+  CK(cudaSetDevice(c->device));
+  CK(launch_sweep_inject(kind, B, N, dt, d_sk, d_truth, d_clc, c->stream, &c->stats));
   return BFL_OK;
 }
 

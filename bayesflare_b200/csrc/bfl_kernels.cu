@@ -3537,9 +3537,17 @@ __global__ void __launch_bounds__(256) k_sweep_simulate(const SimArgs a) {
     int idx = a.H + (int)(ub * (double)(N - 2 * a.H - 1));  // randint(h, N-h-1)
     idx = min(idx, N - a.H - 2);
     next(ua, ub);
-    const double te = 1800.0 + ua * 9000.0;
+    double te = 1800.0 + ua * 9000.0;
     double tg = ub * 5400.0;
-    while (tg > te) { next(ua, ub); tg = ua * 5400.0; }   // redrawn until tau_gauss <= tau_exp
+    if (a.inject != 3) {
+      while (tg > te) { next(ua, ub); tg = ua * 5400.0; }   // redrawn until tau_gauss <= tau_exp (script :321-335)
+    } else {
+      // transit (script :291-312): tauf U[1800, 14400], sigmag U[0, 10800], both redrawn until tauf + 4 sigmag <= 12 h;
+      // recorded as (p1, p2) = (sigmag, tauf)
+      te = 1800.0 + ua * 12600.0;
+      tg = ub * 10800.0;
+      while (te + 4.0 * tg > 43200.0) { next(ua, ub); te = 1800.0 + ua * 12600.0; tg = ub * 10800.0; }
+    }
     next(ua, ub);
     const double snr = a.snr_lo + ua * (a.snr_hi - a.snr_lo);
     par[0] = amp; par[1] = f; par[2] = phase; par[3] = (double)idx; par[4] = te; par[5] = tg; par[6] = snr;
@@ -3549,7 +3557,7 @@ __global__ void __launch_bounds__(256) k_sweep_simulate(const SimArgs a) {
   const int idx = (int)par[3];
   if (a.sinusoid_amp > 0.0)
     for (int i = tid; i < N; i += T) x[i] += amp * sinpi(2.0 * f * ((double)i * a.dt) + phase);
-  if (a.inject) {
+  if (a.inject == 1) {
     const int lo = max(0, idx - 4 * a.H), hi = min(N, idx + 12 * a.H);   // the template is negligible outside
     auto flare = [&](int i) {                                           // Flare.model, models/model.py:197-252
       const double t = (double)(i - idx) * a.dt;
@@ -3566,6 +3574,17 @@ __global__ void __launch_bounds__(256) k_sweep_simulate(const SimArgs a) {
     for (int i = lo + tid; i < hi; i += T) x[i] += flare(i) * scale;
   }
   __syncthreads();
+  if (a.inject >= 2) {
+    // base curve of the script's recipe (noise + sinusoid; the injection is scaled by the noise estimate of THIS
+    // curve and added by k_sweep_inject): no median removal, the script does none for simulated data
+    double* out = a.clc + (size_t)blockIdx.x * N;
+    for (int i = tid; i < N; i += T) out[i] = x[i];
+    if (tid == 0) {
+      double* t = a.truth + (size_t)blockIdx.x * 4;
+      t[0] = (double)idx; t[1] = snr; t[2] = tg; t[3] = te;
+    }
+    return;
+  }
   // median: bitonic sort of a padded copy
   for (int i = tid; i < NP; i += T) srt[i] = i < N ? x[i] : __longlong_as_double(0x7ff0000000000000LL);
   __syncthreads();
@@ -3600,6 +3619,51 @@ cudaError_t launch_sweep_simulate(unsigned long long seed, long long first, int 
   cudaError_t e = cudaFuncSetAttribute(k_sweep_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_sweep_simulate<<<B, 256, smem, s>>>(a);
+  st->launches++;
+  return cudaGetLastError();
+}
+
+// The script's injection (scripts/flare_detection_efficiency.py:444-487): the model at amplitude 1 on the curve's
+// time stamps, rescaled to the drawn signal-to-noise ratio with the noise sigma ESTIMATED from the base curve
+// (sk, tail veto of the Savitzky-Golay residual): clc += inj * snr / ((1/sk) sqrt(sum inj^2)).  One CTA per curve.
+// kind 1: Flare (p1, p2) = (tau_gauss, tau_exp), models/model.py:197-252; kind 2: Transit (p1, p2) = (sigma_g, tau_f),
+// models/model.py:387-436 (amp = 1: -1 inside |t - t0| <= tau_f, Gaussian wings outside).
+__global__ void __launch_bounds__(256) k_sweep_inject(int kind, int N, double dt, const double* __restrict__ sk,
+                                                      const double* __restrict__ truth, double* __restrict__ clc) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ double red[256];
+  const double* t = truth + (size_t)b * 4;
+  const int idx = (int)t[0];
+  if (idx < 0) return;
+  const double snr = t[1], p1 = t[2], p2 = t[3];
+  const double t0 = (double)idx * dt;
+  auto model = [&](int i) {
+    const double ts = (double)i * dt;
+    if (kind == 1) {
+      if (i == idx) return 1.0;
+      const double d = ts - t0;
+      if (i < idx) return p1 > 0.0 ? exp(-(d * d) / (2.0 * (p1 * p1))) : 0.0;
+      return p2 > 0.0 ? exp(-d / p2) : 0.0;
+    }
+    double f = -1.0;
+    if (ts < t0 - p2) { const double x = ts - (t0 - p2); f = p1 > 0.0 ? -exp(-(x * x) / (2.0 * (p1 * p1))) : 0.0; }
+    if (ts > t0 + p2) { const double x = ts - (t0 + p2); f = p1 > 0.0 ? -exp(-(x * x) / (2.0 * (p1 * p1))) : 0.0; }
+    return f;
+  };
+  double s2 = 0.0;
+  for (int i = tid; i < N; i += 256) { const double m = model(i); s2 = fma(m, m, s2); }
+  red[tid] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const double injsnr = (1.0 / sk[b]) * sqrt(red[0]);
+  const double scale = snr / injsnr;
+  double* x = clc + (size_t)b * N;
+  for (int i = tid; i < N; i += 256) x[i] += model(i) * scale;
+}
+
+cudaError_t launch_sweep_inject(int kind, int B, int N, double dt, const double* d_sk, const double* d_truth, double* d_clc,
+                                cudaStream_t s, LaunchStats* st) {
+  k_sweep_inject<<<B, 256, 0, s>>>(kind, N, dt, d_sk, d_truth, d_clc);
   st->launches++;
   return cudaGetLastError();
 }

@@ -74,13 +74,19 @@ def score_host(lnO, inj_idx, snr, threshold, edges):
 
 def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, snr_max=50., seed=0, sinusoid_amp=0.0,
                          detector_kwargs=None, batch=2048, rank=0, world=1, device=None, comm_device="cpu", group=None,
-                         device_sim=False):
+                         device_sim=False, recipe="nstd", inject="flare"):
     """Run the sweep for the realisations owned by ``rank`` and reduce the counters over ranks.
 
     ``device_sim=False``: realisations are simulated on the host (NumPy streams seeded per realisation),
     the detector runs on the device, the bookkeeping on the host.  ``device_sim=True``: everything stays on
     the device -- simulation (``bfl_sweep_simulate_dev``, counter-based Philox streams per realisation),
     noise estimate, detector, matching and histograms (``bfl_sweep_score_dev``); only the counters return.
+
+    ``recipe="script"`` follows the reference script to the letter: ``inject`` = ``"flare"`` or ``"transit"``
+    (``--injtransit``, :291-312, 444-453), the injection is rescaled with the noise sigma ESTIMATED from the base
+    curve by the tail veto (:429-434, 483-487) -- on the device: ``bfl_sweep_simulate_dev`` (base curve + drawn
+    parameters), ``bfl_noise_sigma_dev``, ``bfl_sweep_inject_dev``.  ``recipe="nstd"`` (flares only) scales with the
+    true noise level and removes the median, the bench workloads' convention.
 
     Returns a dict with ``edges`` (SNR bin edges), ``injected`` / ``detected`` (per-bin counts),
     ``efficiency``, ``false_alarms`` (regions that do not hold the injection) and timing."""
@@ -109,12 +115,22 @@ def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, sn
         d_det = torch.zeros(nbins, dtype=torch.int64, device=dev)
         d_cnt = torch.zeros(2, dtype=torch.int64, device=dev)
         spec = det.noise_spec()
+        from ._lib import make_noise_spec
+        spec_script = make_noise_spec("tailveto", det.bglen, det.bgorder, tvsigma=1.0)      # script :429-434
+        d_skb = torch.empty(nbm, dtype=torch.float64, device=dev)
+        kind = 2 if inject == "transit" else 1
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         for first in range(lo, hi, batch):
             nb = min(batch, hi - first)
-            ctx.sweep_simulate_dev(seed, first, nb, N, h, dt, 1.0, sinusoid_amp, 0., snr_max, True,
-                                   d_clc.data_ptr(), d_truth.data_ptr())
+            if recipe == "script":
+                ctx.sweep_simulate_dev(seed, first, nb, N, h, dt, 1.0, sinusoid_amp, 0., snr_max, 1 + kind,
+                                       d_clc.data_ptr(), d_truth.data_ptr())
+                ctx.noise_sigma_dev(spec_script, d_clc.data_ptr(), nb, N, d_skb.data_ptr())
+                ctx.sweep_inject_dev(kind, nb, N, dt, d_skb.data_ptr(), d_truth.data_ptr(), d_clc.data_ptr())
+            else:
+                ctx.sweep_simulate_dev(seed, first, nb, N, h, dt, 1.0, sinusoid_amp, 0., snr_max, 1,
+                                       d_clc.data_ptr(), d_truth.data_ptr())
             ctx.noise_sigma_dev(spec, d_clc.data_ptr(), nb, N, d_sk.data_ptr())
             plan.detector_odds_dev(d_clc.data_ptr(), 0, True, d_sk.data_ptr(), nb, N, 0, N, h, N - h, d_lnO.data_ptr(),
                                    noisepoly=det.noisepoly)
@@ -130,7 +146,8 @@ def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, sn
             nb = min(batch, hi - first)
             t0 = time.perf_counter()
             _, clc, truth = simulate_batch(nb, N, dt=dt, seed=seed, sinusoid_amp=sinusoid_amp, first=first,
-                                           snr_range=(0., snr_max))
+                                           snr_range=(0., snr_max), recipe=recipe,
+                                           inject=(inject if recipe == "script" else True))
             t_sim += time.perf_counter() - t0
             t0 = time.perf_counter()
             lnO = det.oddsratio_batch(clc)                 # [nb, N - 2h], noise sigma estimated on the device
@@ -158,6 +175,9 @@ def main():
     ap.add_argument("--sinusoid-amp", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--device-sim", action="store_true", help="simulate, match and histogram on the device too")
+    ap.add_argument("--recipe", default="nstd", choices=["nstd", "script"],
+                    help="script: injection scaled with the sigma estimated from the base curve, as the reference script does")
+    ap.add_argument("--injtransit", action="store_true", help="inject transits instead of flares (script recipe)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,10 +194,13 @@ def main():
     t0 = time.perf_counter()
     res = detection_efficiency(args.realisations, N=args.samples, threshold=args.threshold, seed=args.seed,
                                sinusoid_amp=args.sinusoid_amp, rank=rank, world=world, device=local_rank,
-                               comm_device=comm_device, device_sim=args.device_sim)
+                               comm_device=comm_device, device_sim=args.device_sim,
+                               recipe="script" if args.injtransit else args.recipe,
+                               inject="transit" if args.injtransit else "flare")
     wall = time.perf_counter() - t0
     if rank == 0:
-        out = {"realisations": res["realisations"], "n_gpus": world, "device_sim": res["device_sim"], "wall_s": wall, "t_detector_s_rank0": res["t_detector_s"],
+        out = {"realisations": res["realisations"], "n_gpus": world, "device_sim": res["device_sim"],
+               "recipe": "script" if args.injtransit else args.recipe, "injection": "transit" if args.injtransit else "flare", "wall_s": wall, "t_detector_s_rank0": res["t_detector_s"],
                "t_simulate_s_rank0": res["t_simulate_s"], "units": res["units"],
                "units_per_s_detector": res["units"] / world / max(res["t_detector_s"], 1e-9) * world,
                "false_alarms": res["false_alarms"],

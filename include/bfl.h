@@ -184,6 +184,11 @@ int bfl_count_regions_total_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, in
  *   out_sk host [B] or NULL: the sigmas used.   *job receives the job number for bfl_pipe_wait.           */
 typedef struct bfl_pipe bfl_pipe;
 typedef struct { int32_t curve, start, stop, argmax; double maxval; } bfl_region;
+/* Region extraction alone, device resident and asynchronous on the context's stream: contiguous_regions of
+ * d_lnO[B][n] > thresh -> d_regions[max_regions] (arbitrary order) and d_counts[B + 3] as described above.
+ * Used by the multi-GPU paths, which gather region records -- not log odds -- over NCCL.                    */
+int bfl_batch_regions_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t n, double thresh, bfl_region* d_regions,
+                          int32_t max_regions, int64_t* d_counts);
 int bfl_pipe_create(bfl_ctx* ctx, bfl_plan* plan, int noisepoly, const bfl_noise_spec* noise, int32_t B, int64_t N,
                     int64_t k0, int64_t k1, int32_t depth, int32_t max_regions, bfl_pipe** pipe);
 int bfl_pipe_submit(bfl_pipe* pipe, const double* clc, const double* sk, double* out_lnO, double thresh,
@@ -198,8 +203,16 @@ int bfl_pipe_destroy(bfl_pipe* pipe);
  *   ranks simulates the same curves whatever the number of ranks): white noise of standard deviation nstd,
  *   optional sinusoid (amplitude U[0, sinusoid_amp] nstd, period 2..31 d), one injected flare (script :321-335:
  *   tau_exp U[1800, 10800], tau_gauss U[0, 5400] redrawn until <= tau_exp, index randint(halfwin, N-halfwin-1),
- *   signal-to-noise U[snr_lo, snr_hi]) when inject != 0, median removed (data.py:271-277).
- *   d_clc dev [B][N] out; d_truth dev [B][4] out: injection index (or -1), snr, tau_gauss, tau_exp.
+ *   signal-to-noise U[snr_lo, snr_hi]) when inject == 1 -- scaled with nstd, median removed (data.py:271-277).
+ *   inject == 2 / 3: the script's own recipe in two steps.  This call returns the BASE curve (noise + sinusoid, no
+ *   median removal) and only draws and records the parameters of a flare (2) or a transit (3; script :291-312:
+ *   tau_f U[1800, 14400], sigma_g U[0, 10800], redrawn until tau_f + 4 sigma_g <= 12 h); the caller estimates the
+ *   noise sigma of the base curve as the script does (:429-434, bfl_noise_sigma_dev with the tail veto) and
+ *   bfl_sweep_inject_dev adds the model rescaled to its signal-to-noise ratio with THAT sigma (:483-487).
+ *   d_clc dev [B][N] out; d_truth dev [B][4] out: injection index (or -1), snr, then (tau_gauss, tau_exp) or
+ *   (sigma_g, tau_f).
+ * bfl_sweep_inject_dev: kind 1 = Flare.model, 2 = Transit.model at amplitude 1 on the whole series;
+ *   d_clc[b] += model * snr / ((1 / d_sk[b]) sqrt(sum model^2)).
  * bfl_sweep_score_dev: above-threshold runs of d_lnO[B][nk] (edge-trimmed by halfwin) expanded by +-2 samples
  *   and merged (script :521-580); the region holding the injection is a detection, every other one a false
  *   positive (:586-612).  ACCUMULATES (arrays not cleared): d_injected / d_detected [nbins] histograms over
@@ -208,6 +221,8 @@ int bfl_pipe_destroy(bfl_pipe* pipe);
 int bfl_sweep_simulate_dev(bfl_ctx* ctx, uint64_t seed, int64_t first, int32_t B, int32_t N, int32_t halfwin, double dt,
                            double nstd, double sinusoid_amp, double snr_lo, double snr_hi, int32_t inject, double* d_clc,
                            double* d_truth);
+int bfl_sweep_inject_dev(bfl_ctx* ctx, int32_t kind, int32_t B, int32_t N, double dt, const double* d_sk,
+                         const double* d_truth, double* d_clc);
 int bfl_sweep_score_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t nk, int32_t halfwin, const double* d_truth,
                         double thresh, int32_t nbins, double snr_max, int64_t* d_injected, int64_t* d_detected,
                         int64_t* d_counters);

@@ -754,6 +754,27 @@ def test_long_series_time_chunks_driver():
     sk = float(det.noise_sigma_batch(x)[0])
     auto, _ = oddsratio_time_chunks(det, x, rank=0, world=1)          # sigma estimated on the device
     np.testing.assert_allclose(auto, np.array(lnO), rtol=1e-10, atol=1e-10)
+    # what the ranks exchange is region records, not log odds: the records of 4 chunks (one region is cut by a
+    # chunk boundary on purpose), joined, are thresholder's segments of the whole series
+    from bayesflare_b200 import longseries
+    thr = 10.0
+    cut = longseries.time_chunks(N, 4, 55, True)[1][0]                # first output sample of chunk 1
+    y = x + orc.flare_model(cts, cts[cut], 40., 500., 2500.)          # a broad, strong flare peaking ON the boundary
+    det2 = bf.OddsRatioDetector(_lc(cts, y))
+    recs = []
+    for r in range(4):
+        run = longseries._runner(det2, N, r, 4)
+        run.run(y, 1.0, thresh=thr)
+        recs.append(run.regions())
+    joined = longseries.join_regions(np.concatenate(recs))
+    whole2, _ = oddsratio_time_chunks(det2, y, sk=1.0, rank=0, world=1)
+    fl, n, mx = det2.thresholder(whole2, thr, expand=0)
+    assert n == len(joined) and n >= 2 and sum(len(r) for r in recs) > n      # a region was split and re-joined
+    np.testing.assert_array_equal(joined[:, :2].astype(int), np.array(fl, dtype=int).reshape(-1, 2))
+    np.testing.assert_array_equal(joined[:, 2].astype(int), [m[1] for m in mx])
+    np.testing.assert_allclose(joined[:, 3], [m[0] for m in mx], rtol=0, atol=2e-12)
+    one, _, _ = longseries.regions_time_chunks(det2, y, thr, sk=1.0)
+    np.testing.assert_array_equal(one[:, :3], joined[:, :3])
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -833,8 +854,11 @@ def test_pipelined_batch_search_matches_blocking_call_and_thresholder():
     det = bf.OddsRatioDetector(_lc(cts, clc[0]))
     plan = det.plan()
     K0, K1 = 27, N - 27
-    lnO_ref, sk_ref = det.oddsratio_batch(clc, return_sk=True)
     depth, nj = 3, 7
+    # every job gets its own input (rows rotated); the blocking call on the same input is the reference
+    # (same kernels, same inputs: bit-identical.  A curve's result may depend on its ROW at the 1e-13 level --
+    # the batched FFT of the noise estimate -- so rotated outputs of one blocking call would not do.)
+    refs = [det.oddsratio_batch(np.roll(clc, j, axis=0), return_sk=True) for j in range(nj)]
     pipe = _lib.Pipe(plan, B, N, K0, K1, noise=det.noise_spec(), depth=depth, max_regions=8 * B)
     h_in = [torch.from_numpy(np.roll(clc, j, axis=0).copy()).pin_memory() for j in range(nj)]
     h_out = [torch.empty((B, K1 - K0), dtype=torch.float64).pin_memory() for _ in range(depth)]
@@ -846,23 +870,22 @@ def test_pipelined_batch_search_matches_blocking_call_and_thresholder():
     for j in range(nj):
         s = j % depth
         if j >= depth:
-            check_job(pipe, jobs[j - depth], j - depth, depth, h_out, h_cnt, h_reg, h_sk, lnO_ref, sk_ref, thr, B, det)
+            check_job(pipe, jobs[j - depth], j - depth, depth, h_out, h_cnt, h_reg, h_sk, refs[j - depth], thr, B, det)
         jobs.append(pipe.submit(h_in[j].data_ptr(), None, h_out[s].data_ptr(), thr, h_reg[s].data_ptr(), h_cnt[s].data_ptr(),
                                 h_sk[s].data_ptr()))
     for j in range(nj - depth, nj):
-        check_job(pipe, jobs[j], j, depth, h_out, h_cnt, h_reg, h_sk, lnO_ref, sk_ref, thr, B, det)
+        check_job(pipe, jobs[j], j, depth, h_out, h_cnt, h_reg, h_sk, refs[j], thr, B, det)
     assert pipe.launches > 0
     with pytest.raises(_lib.BflError):
         pipe.submit(h_in[0].data_ptr(), None, None, float("nan"), None, None)     # nothing to return
 
 
-def check_job(pipe, job, j, depth, h_out, h_cnt, h_reg, h_sk, lnO_ref, sk_ref, thr, B, det):
+def check_job(pipe, job, j, depth, h_out, h_cnt, h_reg, h_sk, ref, thr, B, det):
     nreg = pipe.wait(job)
     s = j % depth
     lnO = h_out[s].numpy()
-    exp = np.roll(lnO_ref, j, axis=0)
-    np.testing.assert_array_equal(lnO, exp)                       # same kernels, same inputs: bit-identical
-    np.testing.assert_array_equal(h_sk[s].numpy(), np.roll(sk_ref, j))
+    np.testing.assert_array_equal(lnO, ref[0])                    # same kernels, same inputs: bit-identical
+    np.testing.assert_array_equal(h_sk[s].numpy(), ref[1])
     cnt = h_cnt[s].numpy()
     rec = np.frombuffer(h_reg[s].numpy().tobytes(), dtype=_lib.REGION_DTYPE)[:nreg]
     rec = np.sort(rec, order=["curve", "start"])
@@ -911,3 +934,63 @@ def test_kepler_search_with_per_star_time_bases_and_a_bad_file(tmp_path):
         recb = batched["Flaring star data"]["KPLR%09d" % kid]
         assert recb["Max. indices"] == rec["Max. indices"]
         np.testing.assert_allclose(recb["Max. odds ratios"], rec["Max. odds ratios"], rtol=1e-4)
+
+
+def test_sweep_script_recipe_injection_on_device_vs_host():
+    """SURVEY 8(f) row f2, the script's recipe to the letter (scripts/flare_detection_efficiency.py:291-335, 429-434,
+    444-453, 483-487): flare AND transit injections rescaled with the noise sigma estimated from the base curve.
+    (i) The device-injected curve equals the host restatement (models.Flare / models.Transit on the whole series,
+    noise.estimate_noise_tv of the Savitzky-Golay residual) applied to the SAME base curve and drawn parameters;
+    (ii) the drawn transit parameters obey the script's constraints; (iii) the all-device sweep with transit
+    injections is independent of the sharding and agrees with the host-simulated sweep within counting errors."""
+    import torch
+    from bayesflare_b200.sweep import detection_efficiency
+    from bayesflare_b200.synthetic import script_injection_scale
+    ctx = _lib.default_context()
+    N, h, B = 1639, 27, 64
+    ts = np.arange(N) * DT
+    spec = _lib.make_noise_spec("tailveto", 55, 4, tvsigma=1.0)
+    for kind, mode in ((1, 2), (2, 3)):
+        d_clc = torch.empty((B, N), dtype=torch.float64, device="cuda")
+        d_t = torch.empty((B, 4), dtype=torch.float64, device="cuda")
+        d_sk = torch.empty(B, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.sweep_simulate_dev(77, 500, B, N, h, DT, 1.0, 2.0, 0., 50., mode, d_clc.data_ptr(), d_t.data_ptr())
+        ctx.sync()
+        base, t = d_clc.cpu().numpy().copy(), d_t.cpu().numpy()
+        ctx.noise_sigma_dev(spec, d_clc.data_ptr(), B, N, d_sk.data_ptr())
+        ctx.sweep_inject_dev(kind, B, N, DT, d_sk.data_ptr(), d_t.data_ptr(), d_clc.data_ptr())
+        ctx.sync()
+        got, sk_dev = d_clc.cpu().numpy(), d_sk.cpu().numpy()
+        idx, snr, p1, p2 = t[:, 0].astype(int), t[:, 1], t[:, 2], t[:, 3]
+        assert idx.min() >= h and idx.max() <= N - h - 2 and snr.min() >= 0 and snr.max() <= 50
+        if kind == 2:
+            assert np.all(p2 + 4 * p1 <= 43200.0) and np.all((p2 >= 1800) & (p2 <= 14400)) and np.all((p1 >= 0) & (p1 <= 10800))
+        else:
+            assert np.all(p1 <= p2) and np.all((p2 >= 1800) & (p2 <= 10800))
+        for b in (0, 5, 33, 63):
+            if kind == 1:
+                inj = bf.Flare(ts, amp=1.).model({"t0": ts[idx[b]], "amp": 1., "taugauss": p1[b], "tauexp": p2[b]})
+            else:
+                inj = bf.Transit(ts, amp=1.).model({"t0": ts[idx[b]], "amp": 1., "sigmag": p1[b], "tauf": p2[b]})
+            fac, sk_host = script_injection_scale(base[b], inj, snr[b])
+            assert abs(sk_dev[b] - sk_host) <= 1e-12 * sk_host
+            want = base[b] + inj * fac
+            np.testing.assert_allclose(got[b], want, rtol=0, atol=1e-11 * max(1.0, np.max(np.abs(want))))
+    whole = detection_efficiency(2048, N=N, seed=6, batch=1024, device_sim=True, recipe="script", inject="transit", sinusoid_amp=2.0)
+    assert whole["injected"].sum() == 2048
+    parts = [detection_efficiency(2048, N=N, seed=6, batch=512, rank=r, world=2, device_sim=True, recipe="script",
+                                  inject="transit", sinusoid_amp=2.0) for r in range(2)]
+    np.testing.assert_array_equal(sum(p["injected"] for p in parts), whole["injected"])
+    np.testing.assert_array_equal(sum(p["detected"] for p in parts), whole["detected"])
+    # the flare detector sees transits mostly at ingress / egress: efficiencies are whatever they are, but device
+    # and host simulations of the same recipe must agree statistically (different random streams)
+    host = detection_efficiency(512, N=N, seed=6, batch=512, recipe="script", inject="transit", sinusoid_amp=2.0)
+    fd = whole["detected"].sum() / whole["injected"].sum()
+    fh = host["detected"].sum() / host["injected"].sum()
+    assert abs(fd - fh) < 0.08, (fd, fh)
+    fl_d = detection_efficiency(1024, N=N, seed=8, batch=1024, device_sim=True, recipe="script", inject="flare")
+    fl_h = detection_efficiency(512, N=N, seed=8, batch=512, recipe="script", inject="flare")
+    ed = fl_d["detected"][20:].sum() / fl_d["injected"][20:].sum()
+    eh = fl_h["detected"][20:].sum() / fl_h["injected"][20:].sum()
+    assert ed > 0.97 and abs(ed - eh) < 0.03
