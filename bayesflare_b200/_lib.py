@@ -112,6 +112,8 @@ SIGNATURES = {
                                 C.POINTER(C.c_int32)]),
     "bfl_pe_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _dp, _dp, C.c_int64, _dp, _dp, C.c_int64, C.c_int32,
                               _dp, C.c_double, C.c_int32, _dp, C.c_int32, _dp]),
+    "bfl_whole_series_lnB": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int64, _dp, _dp, C.c_int64,
+                                       C.c_int32, _dp, _dp, _dp, C.c_double, _dp, _dp]),
     "bfl_logtrapz": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64, _dp]),
     "bfl_fp64_peak_probe": (C.c_int, [C.c_void_p, C.c_int32, _dp, _dp]),
 }
@@ -429,6 +431,24 @@ def pe_grid(ctx, kind, reverse, cts, clc, params, logprior, npoly, polyms, sigma
                               ptr(params), ptr(logprior), G, int(npoly), ptr(polyms), float(sigma),
                               1 if margbackground else 0, ptr(coef), 0 if coef is None else coef.size, ptr(out)))
     return out
+
+
+def whole_series_lnB(ctx, kind, reverse, halfrange, cts, clc, noisevar, params, logprior, bgmodels, bgcross, dbgr,
+                     sumlogsigma, want_bg=False):
+    """``bfl_whole_series_lnB``: log Bayes factors ``[G, N]`` with one polynomial background over the whole series
+    (``params=None``: only the polynomial-only factor).  Returns ``(lnB or None, bg or None)``."""
+    cts, clc, noisevar = f64(cts), f64(clc), f64(noisevar)
+    bgmodels, bgcross, dbgr = f64(bgmodels), f64(bgcross), f64(dbgr)
+    N = cts.size
+    G = 0 if params is None else f64(logprior).size
+    params = None if params is None else f64(params)
+    logprior = None if logprior is None else f64(logprior)
+    out = np.empty((G, N)) if G else None
+    bg = np.zeros(1) if (want_bg or not G) else None
+    check(ctx.lib.bfl_whole_series_lnB(ctx.handle, MODEL_KINDS[kind] if kind else 0, 1 if reverse else 0, 1 if halfrange else 0,
+                                       ptr(cts), ptr(clc), ptr(noisevar), N, ptr(params), ptr(logprior), G, bgmodels.shape[0],
+                                       ptr(bgmodels), ptr(bgcross), ptr(dbgr), float(sumlogsigma), ptr(out), ptr(bg)))
+    return out, (None if bg is None else float(bg[0]))
 
 
 def logtrapz_axis0(ctx, lx, t):

@@ -105,9 +105,11 @@ class Bayes:
         return -0.5 * len(clc) * np.log(2. * pi * var) - np.sum(clc ** 2) / (2. * var)
 
     def _check(self, bglen, nsinusoids):
-        if bglen is None or nsinusoids != 0:
-            raise NotImplementedError("the whole-series background (bglen=None / nsinusoids != 0, "
-                                      "bayes.py:278-307) is not part of the sliding-window GPU path")
+        if nsinusoids != 0:
+            # the reference needs Lightcurve.sinusoid_freqs here, which no Lightcurve defines (bayes.py:278): it raises too
+            raise NotImplementedError("sinusoidal background terms (nsinusoids != 0, bayes.py:278-307) are not supported")
+        if bglen is None:
+            return True
         if bglen % 2 == 0:
             print("Error... Background length (bglen) must be an odd number")      # bayes.py:229-233
             return False
@@ -121,6 +123,8 @@ class Bayes:
         ``ncpus`` is accepted for compatibility and ignored."""
         if not self._check(bglen, nsinusoids):
             return None
+        if bglen is None:
+            return self._whole_series(bgorder, noiseestmethod, psestfrac, tvsigma, halfrange, signal=True)
         sk = estimate_sigma(self.lightcurve, bglen, bgorder, noiseestmethod, psestfrac, tvsigma)
         if sk is None:
             return None
@@ -146,6 +150,8 @@ class Bayes:
         """Log Bayes factor of a polynomial background alone versus Gaussian noise (bayes.py:439-563)."""
         if not self._check(bglen, nsinusoids):
             return None
+        if bglen is None:
+            return self._whole_series(bgorder, noiseestmethod, psestfrac, tvsigma, False, signal=False)
         lc = self.lightcurve
         N = len(lc.cts)
         if bglen > N:
@@ -163,6 +169,45 @@ class Bayes:
             plan.close()
         self.lnBmargBackground = B
         return B
+
+    def _whole_series(self, bgorder, noiseestmethod, psestfrac, tvsigma, halfrange, signal):
+        """``bglen=None`` (bayes.py:292-294, 330-331, 394-395, 408-409): ONE polynomial background over the whole
+        series -- a single Gram matrix -- and the full-length template slid along it.  The series' constants (Gram
+        matrix, data projections, sum of log sigma) are NumPy expressions of the reference taken over as they are;
+        the O(G N^2) template terms and every per-sample marginalisation run on the device
+        (``bfl_whole_series_lnB``).  As in the reference, the light curve must already be detrended: the noise
+        estimate would otherwise ask for a Savitzky-Golay window of ``None`` samples."""
+        lc, model = self.lightcurve, self.model
+        if lc.detrended is False:
+            raise ValueError("bglen=None needs a light curve that is already detrended (the reference's noise estimate "
+                             "calls savitzky_golay with a window of None samples otherwise and raises)")
+        sk = estimate_sigma(lc, None, bgorder, noiseestmethod, psestfrac, tvsigma)
+        if sk is None:
+            return None
+        N = len(lc.cts)
+        npoly = bgorder + 1
+        tsp = np.linspace(0., 1., N)
+        bgmodels = np.array([tsp ** i for i in range(npoly)])
+        noisevar = sk ** 2 + np.asarray(lc.cle, dtype=float) ** 2
+        bgcross = np.zeros((npoly, npoly))
+        for i in range(npoly):
+            for j in range(i, npoly):
+                bgcross[i, j] = np.sum(bgmodels[i] * bgmodels[j] / noisevar)
+        d = np.asarray(lc.clc, dtype=float) / noisevar
+        dbgr = np.array([np.sum(d * bgmodels[i]) for i in range(npoly)])
+        ctx = _lib.default_context()
+        if not signal:
+            _, bg = _lib.whole_series_lnB(ctx, None, False, False, lc.cts, lc.clc, noisevar, None, None, bgmodels, bgcross,
+                                          dbgr, _sumlogsigma(noisevar))
+            self.lnBmargBackground = np.full(N, bg)
+            return self.lnBmargBackground
+        if model.device_kind is None:
+            raise NotImplementedError("bglen=None supports the built-in models")
+        hyp = hypothesis_from_model(model, np.asarray(model.ts, dtype=float), halfrange, ranges=self.ranges)
+        lnB, _ = _lib.whole_series_lnB(ctx, hyp["kind"], hyp["reverse"], halfrange, model.ts, lc.clc, noisevar, hyp["params"],
+                                       hyp["logprior"], bgmodels, bgcross, dbgr, _sumlogsigma(noisevar))
+        self.lnBmargAmp = lnB.reshape(tuple(model.shape) + (N,))
+        self.premarg = np.copy(self.lnBmargAmp)
 
     def marginalise(self, pname):
         """Integrate ``lnBmargAmp`` over one parameter with the log-space trapezium rule, or drop

@@ -1150,6 +1150,60 @@ int bfl_pe_grid(bfl_ctx* c, int32_t kind, int32_t reverse, const double* cts, co
   return BFL_OK;
 }
 
+// --------------------------------------------------------------------------------------
+int bfl_whole_series_lnB(bfl_ctx* c, int32_t kind, int32_t reverse, int32_t halfrange, const double* cts, const double* clc,
+                         const double* noisevar, int64_t N, const double* params, const double* logprior, int64_t G,
+                         int32_t P, const double* bgmodels, const double* bgcross, const double* dbgr, double sumlogsigma,
+                         double* out_lnB, double* out_bg) {
+  if (!c || !cts || !clc || !noisevar || !bgmodels || !bgcross || !dbgr || (G > 0 && (!params || !logprior || !out_lnB)) ||
+      (G <= 0 && !out_bg))
+    return fail(BFL_ERR_ARG, "null argument to bfl_whole_series_lnB");
+  if (G < 0) G = 0;
+  if (kind < 0 || kind >= BFL_MODEL_TABLE) return fail(BFL_ERR_ARG, "bad model kind");
+  if (P < 1 || P > MAXP) return fail(BFL_ERR_UNSUPPORTED, "bgorder must be in 0..5");
+  if (N < 3 || N > (1 << 20)) return fail(BFL_ERR_UNSUPPORTED, "the whole-series background supports 3 .. 2^20 samples");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int NP = (int)((N + 1) & ~(int64_t)1);
+  std::vector<TemplDesc> desc((size_t)G);
+  for (int64_t g = 0; g < G; g++) {
+    desc[g].kind = kind; desc[g].reverse = reverse;
+    for (int i = 0; i < 4; i++) desc[g].p[i] = params[(size_t)g * 4 + i];
+  }
+  std::vector<double> abg((size_t)P * N), dt((size_t)N);
+  for (int j = 0; j < P; j++)
+    for (int64_t n = 0; n < N; n++) abg[(size_t)j * N + n] = bgmodels[(size_t)j * N + n] / noisevar[n];   // bayes.py:394
+  for (int64_t n = 0; n < N; n++) dt[n] = clc[n] / noisevar[n];                                              // bayes.py:403
+  void *d_desc, *d_cts, *d_tm, *d_abg, *d_dt, *d_v, *d_bgc, *d_dbg, *d_lp, *d_out, *d_obg;
+  int rc;
+  if ((rc = c->get("ws_obg", sizeof(double), &d_obg))) return rc;
+  if ((rc = c->get("ws_desc", sizeof(TemplDesc) * (size_t)std::max<int64_t>(G, 1), &d_desc)) || (rc = c->get("ws_cts", sizeof(double) * (size_t)N, &d_cts)) ||
+      (rc = c->get("ws_tm", sizeof(double) * (size_t)std::max<int64_t>(G, 1) * NP, &d_tm)) || (rc = c->get("ws_abg", sizeof(double) * (size_t)P * N, &d_abg)) ||
+      (rc = c->get("ws_dt", sizeof(double) * (size_t)N, &d_dt)) || (rc = c->get("ws_v", sizeof(double) * (size_t)N, &d_v)) ||
+      (rc = c->get("ws_bgc", sizeof(double) * MAXP * MAXP, &d_bgc)) || (rc = c->get("ws_dbg", sizeof(double) * MAXP, &d_dbg)) ||
+      (rc = c->get("ws_lp", sizeof(double) * (size_t)std::max<int64_t>(G, 1), &d_lp)) ||
+      (rc = c->get("ws_out", sizeof(double) * (size_t)std::max<int64_t>(G, 1) * N, &d_out)))
+    return rc;
+  if (G > 0) CK(cudaMemcpyAsync(d_desc, desc.data(), sizeof(TemplDesc) * (size_t)G, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_cts, cts, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_abg, abg.data(), sizeof(double) * (size_t)P * N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_dt, dt.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_v, noisevar, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_bgc, bgcross, sizeof(double) * (size_t)P * P, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_dbg, dbgr, sizeof(double) * (size_t)P, cudaMemcpyHostToDevice, s));
+  if (G > 0) {
+    CK(cudaMemcpyAsync(d_lp, logprior, sizeof(double) * (size_t)G, cudaMemcpyHostToDevice, s));
+    CK(launch_gen_templates((const TemplDesc*)d_desc, (int)G, (const double*)d_cts, (int)N, NP, (double*)d_tm, s, &c->stats));
+  }
+  CK(launch_whole_series(P, (const double*)d_tm, (const double*)d_abg, (const double*)d_dt, (const double*)d_v,
+                         (const double*)d_bgc, (const double*)d_dbg, (const double*)d_lp, (int)N, NP, (int)G,
+                         halfrange ? 1 : 0, sumlogsigma, (double*)d_out, out_bg ? (double*)d_obg : nullptr, s, &c->stats));
+  if (G > 0) CK(cudaMemcpyAsync(out_lnB, d_out, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToHost, s));
+  if (out_bg) CK(cudaMemcpyAsync(out_bg, d_obg, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));   // also keeps the host staging vectors alive until the copies are done
+  return BFL_OK;
+}
+
 int bfl_logtrapz(bfl_ctx* c, const double* lx, const double* t, int64_t n, int64_t m, double* out) {
   if (!c || !lx || !t || !out || n < 1 || m < 1) return fail(BFL_ERR_ARG, "bad argument to bfl_logtrapz");
   CK(cudaSetDevice(c->device));

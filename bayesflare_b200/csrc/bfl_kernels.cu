@@ -1944,6 +1944,94 @@ __device__ __forceinline__ double signal_logL(const BgElim<P>& e, const double (
   return logL;
 }
 
+// --------------------------------------------------------------------------------------
+// WHOLE-SERIES background (bglen = None, nsinusoids = 0; stats/bayes.py:247-437, the `else` branches at
+// :292-294, 330-331, 394-395, 408-409): ONE polynomial background over all N samples -- its Gram matrix and data
+// projections are constants of the series (the caller computes them exactly as the reference does, np.sum) --
+// and the full-length template slid along the series: for sample k the template's centre sample m[N/2] sits on k,
+// truncated to the series.  Per (template, sample): P + 2 dot products over the overlap, then the reference's
+// elimination (log_marg_amp_full.c:29-66) in its own order.  One thread per sample, blockIdx.y = template.
+struct WholeArgs {
+  const double* tm;      // [G][NP] templates on the series' time stamps
+  const double* abg;     // [P][N]  bgmodels[j] / noisevar            (bayes.py:394)
+  const double* dt;      // [N]     clc / noisevar                     (bayes.py:403)
+  const double* v;       // [N]     noisevar
+  const double* bgcross; // [P][P]  upper triangle used               (bayes.py:330-331)
+  const double* dbgr;    // [P]                                        (bayes.py:408-409)
+  const double* lp;      // [G] log prior + amplitude prior; -inf rows are skipped
+  int N, NP, G, half;
+  double sls;            // sumlogsigma (general.pyx:216-221)
+  double* out;           // [G][N]
+  double* out_bg;        // [1] or nullptr: the polynomial-only factor (bayes.py:439-563; constant along the series)
+};
+
+template <int P>
+__global__ void __launch_bounds__(128) k_whole_series(const WholeArgs a) {
+  const int g = blockIdx.y;
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int N = a.N;
+  if (k >= N) return;
+  double M[P][P], D[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) {
+    D[i] = a.dbgr[i];
+#pragma unroll
+    for (int j = 0; j < P; j++) M[i][j] = a.bgcross[i * P + j];      // upper triangle is what the elimination reads
+  }
+  BgElim<P> e;
+  bg_eliminate<P>(e, M, D);
+  if (a.out_bg && g == 0 && k == 0) *a.out_bg = bg_only_logL<P>(e) + a.sls;
+  if (a.G == 0) return;
+  const double lp = a.lp[g];
+  double* out = a.out + (size_t)g * N + k;
+  if (!(lp > -INFINITY)) { *out = neg_inf(); return; }      // bayes.py:358-363: the row stays -inf
+  const int h = N / 2;                                       // nsteps = int(N / 2)
+  const double* m = a.tm + (size_t)g * a.NP;
+  // np.correlate(x, m, 'same')[k] = sum_n x[n] m[n - k + h]
+  const int n0 = max(0, k - h), n1 = min(N - 1, k - h + N - 1);
+  double x[P], dm = 0.0;
+#pragma unroll
+  for (int j = 0; j < P; j++) x[j] = 0.0;
+  for (int n = n0; n <= n1; n++) {
+    const double mv = m[n - k + h];
+#pragma unroll
+    for (int j = 0; j < P; j++) x[j] = fma(a.abg[(size_t)j * N + n], mv, x[j]);
+    dm = fma(a.dt[n], mv, dm);
+  }
+  // mdcross (bayes.py:367-377) with the reference's own slices: k < h: m[h-k:] on v[:len]; k >= N-h: m[:N-h-k-1] on
+  // v[-len:] -- for an even N that places the template one sample late; the single middle sample of an odd N: all of it
+  double mm = 0.0;
+  {
+    int mi0, s0, len;
+    if (k < h) { mi0 = h - k; s0 = 0; len = N - mi0; }
+    else if (k >= N - h) { mi0 = 0; len = 2 * N - h - k - 1; s0 = N - len; }   // the stop N-h-k-1 is negative: N + stop elements
+    else { mi0 = 0; s0 = k - h; len = N; }
+    for (int i = 0; i < len; i++) {
+      const double mv = m[mi0 + i];
+      mm = add_(mm, div_(mul_(mv, mv), a.v[s0 + i]));
+    }
+  }
+  *out = (signal_logL<P>(e, x, mm, dm, a.half != 0) + a.sls) + lp;
+}
+
+cudaError_t launch_whole_series(int P, const double* d_tm, const double* d_abg, const double* d_dt, const double* d_v,
+                                const double* d_bgcross, const double* d_dbgr, const double* d_lp, int N, int NP, int G,
+                                int half, double sls, double* d_out, double* d_out_bg, cudaStream_t s, LaunchStats* st) {
+  WholeArgs a{d_tm, d_abg, d_dt, d_v, d_bgcross, d_dbgr, d_lp, N, NP, G, half, sls, d_out, d_out_bg};
+  const dim3 grid((unsigned)(G > 0 ? (N + 127) / 128 : 1), (unsigned)(G > 0 ? G : 1));
+  switch (P) {
+    case 1: k_whole_series<1><<<grid, 128, 0, s>>>(a); break;
+    case 2: k_whole_series<2><<<grid, 128, 0, s>>>(a); break;
+    case 3: k_whole_series<3><<<grid, 128, 0, s>>>(a); break;
+    case 4: k_whole_series<4><<<grid, 128, 0, s>>>(a); break;
+    case 5: k_whole_series<5><<<grid, 128, 0, s>>>(a); break;
+    case 6: k_whole_series<6><<<grid, 128, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  st->launches++;
+  return cudaGetLastError();
+}
+
 struct GenArgs {
   const double* dw;     // [B][seglen]
   const double* uu;     // [B][seglen] noise variance v

@@ -132,6 +132,9 @@ cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scr
 cudaError_t launch_combine(const PlanView& pv, const SeriesView& sv, const Scratch& sc, int noisepoly,
                            double* d_lnO, double* d_marg, cudaStream_t s, LaunchStats* st);
 
+cudaError_t launch_whole_series(int P, const double* d_tm, const double* d_abg, const double* d_dt, const double* d_v,
+                                const double* d_bgcross, const double* d_dbgr, const double* d_lp, int N, int NP, int G,
+                                int half, double sls, double* d_out, double* d_out_bg, cudaStream_t s, LaunchStats* st);
 cudaError_t launch_pe_grid(int kind, int reverse, const double* d_cts, const double* d_clc, int L,
                            const double* d_params, const double* d_logprior, int64_t G, int P,
                            const double* d_polyms, double sigma, int margbackground, double* d_post,

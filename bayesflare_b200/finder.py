@@ -200,6 +200,8 @@ class OddsRatioDetector:
         """Time series of the log odds ratio (find.py:741-864).  Returns ``(lnO, ts)`` with
         ``lnO`` a list of floats, as the reference does."""
         lc = self.lightcurve
+        if self.bglen is None and self.nsinusoids == 0:
+            return self._oddsratio_whole_series()
         plan = self.plan()
         if plan is None:
             return None
@@ -229,6 +231,37 @@ class OddsRatioDetector:
             noisevar = sk ** 2 + cle ** 2
             lnO = lnO + float(np.sum(np.log(np.sqrt(noisevar))))
         return np.asarray(lnO).ravel().tolist(), np.copy(lc.cts[h:N - h])
+
+    def _oddsratio_whole_series(self):
+        """``bglen=None``: every hypothesis with ONE polynomial background over the whole series
+        (``Bayes._whole_series`` -> ``bfl_whole_series_lnB``), marginalised with the device log-trapezium rule and
+        folded exactly as find.py:774-864 does.  No edges are dropped (find.py:846-851 needs a ``bglen``)."""
+        from .bayes import Bayes
+        from .general import logplus
+        lc = self.lightcurve
+        kw = dict(bglen=None, bgorder=self.bgorder, nsinusoids=0, noiseestmethod=self.noiseestmethod,
+                  psestfrac=self.psestfrac, tvsigma=self.tvsigma)
+        models = self.hypotheses(lc.cts)
+        Bf = Bayes(lc, models[0][0])
+        if Bf.bayes_factors_marg_poly_bgd(**kw) is None and getattr(Bf, "lnBmargAmp", None) is None:
+            return None
+        Of = Bf.marginalise_full().lnBmargAmp
+        noiseodds = []
+        if self.noisepoly:
+            noiseodds.append(Bf.bayes_factors_marg_poly_bgd_only(bglen=None, bgorder=self.bgorder, nsinusoids=0,
+                                                                 noiseestmethod=self.noiseestmethod,
+                                                                 psestfrac=self.psestfrac, tvsigma=self.tvsigma))
+        for m, hr in models[1:]:
+            B = Bayes(lc, m)
+            B.bayes_factors_marg_poly_bgd(halfrange=hr, **kw)
+            noiseodds.append(B.marginalise_full().lnBmargAmp)
+        lnO = []
+        for i in range(len(Of)):
+            denom = -np.inf
+            for n in noiseodds:
+                denom = logplus(denom, n[i])
+            lnO.append(Of[i] - denom if noiseodds else Of[i])
+        return lnO, np.copy(lc.cts)
 
     def noise_spec(self, detrended=False):
         """Device-side description of this detector's noise estimate (``bfl_noise_spec``)."""

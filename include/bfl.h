@@ -248,6 +248,22 @@ int bfl_pe_grid(bfl_ctx* ctx, int32_t kind, int32_t reverse, const double* cts, 
                 const double* polyms, double sigma, int32_t margbackground, const double* sgcoef, int32_t sgbins,
                 double* out_post);
 
+/* ---- Bayes.bayes_factors_marg_poly_bgd with bglen = None, nsinusoids = 0 (bayes.py:247-437, the whole-series
+ * branches :292-294, 330-331, 394-395, 408-409): ONE polynomial background over all N samples, the full-length
+ * template slid along the series.  Replaces the same Cython/C chain as bfl_window_lnB.
+ *   cts, clc, noisevar host [N] (noisevar = sk^2 + cle^2, bayes.py:312)
+ *   params host [G][4], logprior host [G] (Model.prior + log amplitude prior; -inf rows stay -inf)
+ *   bgmodels host [P][N] = linspace(0,1,N)**p as the caller's NumPy computed it (bayes.py:292-307)
+ *   bgcross host [P][P] (upper triangle) = np.sum(bg_i bg_j / noisevar), dbgr host [P] = np.sum(clc / noisevar * bg_i):
+ *   constants of the series, computed by the caller with NumPy exactly as the reference does
+ *   out_lnB host [G][N] (may be NULL when G == 0)
+ *   out_bg  host [1] or NULL: the polynomial-only factor of bayes_factors_marg_poly_bgd_only (bayes.py:439-563),
+ *           one number: with a whole-series background it is the same for every sample                           */
+int bfl_whole_series_lnB(bfl_ctx* ctx, int32_t kind, int32_t reverse, int32_t halfrange, const double* cts, const double* clc,
+                         const double* noisevar, int64_t N, const double* params, const double* logprior, int64_t G,
+                         int32_t P, const double* bgmodels, const double* bgcross, const double* dbgr, double sumlogsigma,
+                         double* out_lnB, double* out_bg);
+
 /* ---- logtrapz (general.pyx:576-607) over the leading axis of lx[n][m] -> out[m] ------ */
 int bfl_logtrapz(bfl_ctx* ctx, const double* lx, const double* t, int64_t n, int64_t m, double* out);
 

@@ -451,6 +451,78 @@ def background_only(clc, cle, cts, sk, bglen=55, bgorder=4):
     return out
 
 
+def _marg_full(M, D, lhr):
+    M, D = _f64(M), _f64(D)
+    return lib().orc_marg_full(len(D), _p(M), _p(D), 1.0, 1 if lhr else 0)
+
+
+def bayes_factors_whole_series(clc, cle, cts, mtype, paramranges, sk, bgorder=4, halfrange=True, reverse=False,
+                               with_background=False):
+    """``Bayes.bayes_factors_marg_poly_bgd(bglen=None, nsinusoids=0)`` (stats/bayes.py:247-437 with the `else`
+    branches at :292-294, 330-331, 394-395, 408-409): ONE polynomial background over the whole series -- global
+    Gram matrix and data projections, constant along the series -- and the full-length template slid along it
+    with the reference's own truncation slices (:367-377; for an even number of samples the end branch places
+    the template one sample late, kept).  np.correlate / np.sum as the reference calls them; the per-sample
+    elimination is the C restatement (log_marg_amp_full.c:3-68)."""
+    clc, cle, cts = _f64(clc), _f64(cle), _f64(cts)
+    N = len(cts)
+    nsteps = int(N / 2)
+    P = bgorder + 1
+    Nm = P + 1
+    ranges, shape = make_ranges(mtype, paramranges)
+    names = MODEL_PARAMNAMES[mtype]
+    G = int(np.prod(shape))
+    L = lib()
+    L.orc_marg_full.restype = C.c_double
+    L.orc_marg_full.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_int]
+    tsp = np.linspace(0., 1., N)
+    bg = np.array([tsp ** i for i in range(P)])
+    v = sk ** 2 + cle ** 2
+    bgcross = np.zeros((P, P))
+    for i in range(P):
+        for j in range(i, P):
+            bgcross[i, j] = np.sum(bg[i] * bg[j] / v)
+    d = clc / v
+    dbgr = np.array([np.sum(d * bg[i]) for i in range(P)])
+    sumlogsigma = np.sum(np.log(np.sqrt(v)[np.isfinite(np.sqrt(v))]))
+    lnB = np.full((G, N), -np.inf)
+    ampprior = np.log(0.5) if halfrange else 0.
+    for g in range(G):
+        q = np.unravel_index(g, shape)
+        pd = {names[k]: ranges[names[k]][q[k]] for k in range(len(names))}
+        prior = model_prior(mtype, pd, ranges)
+        if prior == -np.inf:
+            continue
+        m = eval_model(mtype, pd, cts, reverse)
+        mdcross = np.empty(N)
+        for k in range(N):
+            if k < nsteps:
+                mm = m[nsteps - k:] ** 2
+                mm = mm / v[:len(mm)]
+            elif k >= N - nsteps:
+                mm = m[:(N - nsteps - k - 1)] ** 2
+                mm = mm / v[-len(mm):] if len(mm) else mm
+            else:
+                mm = m ** 2 / v[k - nsteps:k + nsteps + 1]
+            mdcross[k] = np.sum(mm)
+        mdbg = np.array([np.correlate(bg[j] / v, m, 'same') for j in range(P)])
+        dm = np.correlate(d, m, 'same')
+        M = np.zeros((Nm, Nm))
+        M[:P, :P] = bgcross
+        D = np.zeros(Nm)
+        D[:P] = dbgr
+        for k in range(N):
+            M[:P, P] = mdbg[:, k]
+            M[P, P] = mdcross[k]
+            D[P] = dm[k]
+            lnB[g, k] = _marg_full(M, D, halfrange) + sumlogsigma
+        lnB[g] += prior + ampprior
+    lnB = lnB.reshape(tuple(shape) + (N,))
+    if with_background:
+        return lnB, ranges, np.full(N, _marg_full(bgcross, dbgr, False) + sumlogsigma)
+    return lnB, ranges
+
+
 def marginalise_full(lnB, ranges, names):
     """``Bayes.marginalise_full`` (stats/bayes.py:565-621): for every parameter in order,
     drop a singleton axis or apply ``logtrapz`` along it."""

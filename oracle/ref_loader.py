@@ -58,6 +58,8 @@ PATCHES = {
     "bayesflare.stats.bayes": [
         ("self.posterior == None", "self.posterior is None", 3),
         ("self.maxposterior == None", "self.maxposterior is None", 2),
+        # Python 2 orders None below every int, so `None > N` is simply False there (bglen=None path, row f3)
+        ("if bglen > N:", "if bglen is not None and bglen > N:", 1),
     ],
 }
 

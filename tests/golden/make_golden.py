@@ -358,6 +358,42 @@ def gold_transit5(bf):
          sigmag=np.array(ranges["sigmag"]), tauf=np.array(ranges["tauf"]))
 
 
+def gold_whole(bf):
+    """SURVEY row f3, the executable half: bglen=None, nsinusoids=0 -- ONE polynomial background over the whole
+    series (a single global Gram matrix), the template slid along it (bayes.py:247-437 with the `else` branches
+    at :292-294, 330-331, 394-395, 408-409).  The reference only gets there with an already detrended light curve
+    (otherwise it asks savitzky_golay for a window of None samples and raises), so `detrended` is set by hand."""
+    out = {}
+    import importlib
+    rb = importlib.import_module("bayesflare.stats.bayes")
+    keep = (rb.estimate_noise_ps, rb.estimate_noise_tv)
+    try:
+        for tag, N, bgorder in (("odd", 301, 4), ("even", 300, 2)):
+            rng = np.random.RandomState(1300 + N)
+            ts = np.arange(N) * DT_LONG
+            clc = rng.randn(N) + ref_flare(bf, ts, ts[170], 7., 1200., 3000.) + 0.8 * (ts / ts[-1]) ** 2
+            cle = 0.2 + 0.1 * rng.rand(N)
+            sk = 0.93
+            _force_sk_detector(sk)
+            lc = ref_loader.RefLightcurve(ts, clc, cle)
+            lc.detrended = True
+            out.update({tag + "_cts": ts, tag + "_clc": clc, tag + "_cle": cle, tag + "_sk": np.array(sk),
+                        tag + "_bgorder": np.array(bgorder)})
+            for name, mk, hr in (("flare", lambda: bf.Flare(ts, amp=1, paramranges={"t0": (np.inf,), "taugauss": (0, 5400, 3),
+                                                                                  "tauexp": (1800, 10800, 3), "amp": (1.,)}), True),
+                                 ("expdecay", lambda: bf.Expdecay(ts, amp=1, paramranges={"t0": (np.inf,), "tauexp": (0., 900., 3),
+                                                                                        "amp": (1.,)}), True),
+                                 ("step", lambda: bf.Step(ts, amp=1, paramranges={"t0": (np.inf,), "amp": (1.,)}), False)):
+                B = bf.Bayes(lc, mk())
+                B.bayes_factors_marg_poly_bgd(bglen=None, bgorder=bgorder, halfrange=hr)
+                out["ref_%s_lnB_%s" % (tag, name)] = B.lnBmargAmp
+                out["ref_%s_marg_%s" % (tag, name)] = B.marginalise_full().lnBmargAmp
+            out["ref_%s_bgonly" % tag] = B.bayes_factors_marg_poly_bgd_only(bglen=None, bgorder=bgorder)
+    finally:
+        rb.estimate_noise_ps, rb.estimate_noise_tv = keep
+    save("whole", **out)
+
+
 def gold_ingest(bf):
     """Ingest conditioning + Kepler-search detector on a file-like light curve (float32 flux with NaN
     gaps, per-sample float32 errors): data.py:240-277, 279-351; scripts/kepler_analysis_script.py:376-382.
@@ -403,7 +439,9 @@ def gold_ingest(bf):
 def main():
     bf = ref_loader.load_reference()
     which = sys.argv[1:] or ["scalars", "elimination", "kat200", "detector", "config1", "shortcad", "pegrid", "ingest",
-                             "trend", "transit5"]
+                             "trend", "transit5", "whole"]
+    if "whole" in which:
+        gold_whole(bf)
     if "trend" in which:
         gold_trend(bf)
     if "transit5" in which:

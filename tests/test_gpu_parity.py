@@ -994,3 +994,52 @@ def test_sweep_script_recipe_injection_on_device_vs_host():
     ed = fl_d["detected"][20:].sum() / fl_d["injected"][20:].sum()
     eh = fl_h["detected"][20:].sum() / fl_h["injected"][20:].sum()
     assert ed > 0.97 and abs(ed - eh) < 0.03
+
+
+WHOLE_MODELS = {
+    "flare": (bf.Flare, {"t0": (np.inf,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3), "amp": (1.,)}, True),
+    "expdecay": (bf.Expdecay, {"t0": (np.inf,), "tauexp": (0., 900., 3), "amp": (1.,)}, True),
+    "step": (bf.Step, {"t0": (np.inf,), "amp": (1.,)}, False),
+}
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_whole_series_background_vs_reference(tag, monkeypatch):
+    """SURVEY row f3, the executable half: bglen=None, nsinusoids=0 (bayes.py:292-294, 330-331, 394-395, 408-409) --
+    one polynomial background over the whole series, the template slid along it -- against the reference's own
+    output (tests/golden/whole.npz; odd and even series lengths: the reference's end slices place the template one
+    sample late for an even length, and some samples are NaN where the truncated template is empty or zero).
+    Also the detector built on it (find.py:741-864 with bglen=None: no edges dropped)."""
+    g = load_golden("whole")
+    cts, clc, cle, sk, bgorder = g[tag + "_cts"], g[tag + "_clc"], g[tag + "_cle"], float(g[tag + "_sk"]), int(g[tag + "_bgorder"])
+    _force_sk(monkeypatch, sk)
+    lc = _lc(cts, clc, cle)
+    with pytest.raises(ValueError):            # the reference raises too unless the curve is already detrended
+        bf.Bayes(lc, bf.Step(cts, amp=1, paramranges=dict(WHOLE_MODELS["step"][1]))).bayes_factors_marg_poly_bgd(bglen=None)
+    lc.detrended = True
+    marg = {}
+    for name, (cls, pr, hr) in WHOLE_MODELS.items():
+        B = bf.Bayes(lc, cls(cts, amp=1, paramranges=dict(pr)))
+        B.bayes_factors_marg_poly_bgd(bglen=None, bgorder=bgorder, halfrange=hr)
+        assert_logodds_close(B.lnBmargAmp, g["ref_%s_lnB_%s" % (tag, name)], TOL, "whole-series " + name)
+        marg[name] = B.marginalise_full().lnBmargAmp
+        assert_logodds_close(marg[name], g["ref_%s_marg_%s" % (tag, name)], TOL, "whole-series marginal " + name)
+    bgo = B.bayes_factors_marg_poly_bgd_only(bglen=None, bgorder=bgorder)
+    assert_logodds_close(bgo, g["ref_%s_bgonly" % tag], TOL, "whole-series polynomial only")
+    with pytest.raises(NotImplementedError):
+        B.bayes_factors_marg_poly_bgd(bglen=None, nsinusoids=2)
+    det = bf.OddsRatioDetector(lc, bglen=None, bgorder=bgorder, flareparams=dict(WHOLE_MODELS["flare"][1]),
+                               noiseimpulse=False, noiseexpdecay=True, noiseexpdecayparams={"tauexp": (0., 900., 3)},
+                               noiseexpdecaywithreverse=False, noisestep=True)
+    lnO, ts = det.oddsratio()
+    assert len(lnO) == len(cts) and np.array_equal(ts, cts)
+    want = []
+    for i in range(len(cts)):
+        den = -np.inf
+        for arr in (g["ref_%s_bgonly" % tag], g["ref_%s_marg_expdecay" % tag], g["ref_%s_marg_step" % tag]):
+            den = orc.logplus(den, arr[i])
+        want.append(g["ref_%s_marg_flare" % tag][i] - den)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(lnO), fin)
+    err = np.abs(np.array(lnO)[fin] - np.array(want)[fin]) / np.maximum(1.0, np.abs(np.array(want)[fin]))
+    assert err.max() <= TOL, err.max()

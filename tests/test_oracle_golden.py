@@ -161,3 +161,17 @@ def test_oracle_transit_odds_config5_shape():
     ranges = {"t0": (np.inf,), "sigmag": (sg[0], sg[1], int(sg[2])), "tauf": (tf[0], tf[1], int(tf[2])), "amp": (1.,)}
     lnB, _ = orc.bayes_factors(g["clc"], np.zeros(len(g["clc"])), g["cts"], "transit", ranges, float(g["ref_sk"]))
     assert_logodds_close(lnB, g["ref_lnB"], 1e-9, "oracle transit lnB")
+
+
+def test_oracle_whole_series_background():
+    """Row f3 (bglen=None, nsinusoids=0): the restatement against the reference's own output, odd and even lengths."""
+    g = load_golden("whole")
+    cases = (("flare", {"t0": (np.inf,), "taugauss": (0, 5400, 3), "tauexp": (1800, 10800, 3), "amp": (1.,)}, True),
+             ("expdecay", {"t0": (np.inf,), "tauexp": (0., 900., 3), "amp": (1.,)}, True),
+             ("step", {"t0": (np.inf,), "amp": (1.,)}, False))
+    for tag in ("odd", "even"):
+        cts, clc, cle, sk, bo = g[tag + "_cts"], g[tag + "_clc"], g[tag + "_cle"], float(g[tag + "_sk"]), int(g[tag + "_bgorder"])
+        for name, pr, hr in cases:
+            lnB, _, bgo = orc.bayes_factors_whole_series(clc, cle, cts, name, pr, sk, bgorder=bo, halfrange=hr, with_background=True)
+            assert_logodds_close(lnB, g["ref_%s_lnB_%s" % (tag, name)], 1e-12, "%s %s" % (tag, name))
+        assert_logodds_close(bgo, g["ref_%s_bgonly" % tag], 1e-12, tag + " bgonly")
