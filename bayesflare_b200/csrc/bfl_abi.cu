@@ -287,7 +287,7 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
   struct SubC { int a0, na, c; };
   std::vector<SubC> sub_c;                 // per separable hypothesis: first A row, number of A rows, C row
   int S = 0;
-  bool sep_ok = (W == 55);
+  bool sep_ok = split_window_supported(W);
   for (int h = 0; h < nhyp && sep_ok; h++) {
     const int g0 = pv.hyp_begin[h], g1 = pv.hyp_begin[h + 1];
     pv.hyp_A0[h] = 0; pv.hyp_nA[h] = 0;

@@ -729,10 +729,12 @@ struct CorrArgs {
   double* Y;            // [S][B * nk]
 };
 
-template <int KT>
-__global__ void __launch_bounds__(FAST_TPB, 3) k_corr_shapes(const CorrArgs a) {
+// W is a compile-time window length (the register window holds W + KT - 1 samples): instantiated for the odd
+// lengths the reference's scripts use (21, 33, 55) and 101; other lengths take the single-kernel path.
+template <int W, int KT>
+__global__ void __launch_bounds__(FAST_TPB, (W + KT - 1 > 64) ? 2 : 3) k_corr_shapes(const CorrArgs a) {
   extern __shared__ double smem[];
-  constexpr int W = 55, H = W / 2, TKW = 32 * KT;
+  constexpr int H = W / 2, TKW = 32 * KT;
   const int WP = a.WP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int wstride = (TKW + 2 * H + 2) & ~1;
@@ -1477,15 +1479,18 @@ static size_t epi2_smem_bytes(int G, int S, int srows) {
   return (size_t)Epi2Layout(G, S).plan_bytes + sizeof(double) * (size_t)srows * EPI2_TPB;
 }
 bool epi2_fits(const PlanView& pv) {   // one sample per thread: the slice must fit four times per SM
-  return pv.sep_ok && pv.wsep_ok && pv.W == 55 && pv.G > 0 && pv.nhyp >= 1 && pv.hyp_begin[1] > 0 &&
+  return pv.sep_ok && pv.wsep_ok && split_window_supported(pv.W) && pv.G > 0 && pv.nhyp >= 1 && pv.hyp_begin[1] > 0 &&
          epi2_smem_bytes(pv.G, pv.S, epi2_srows(pv)) <= 56 * 1024;
 }
 size_t epi2_plan_block_bytes(const PlanView& pv) { return (size_t)Epi2Layout(pv.G, pv.S).plan_bytes; }
 
-static size_t corr_smem_bytes(int S, int KT) {
-  const int wstride = (32 * KT + 2 * 27 + 2) & ~1;
-  return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)S * 56);
+static size_t corr_smem_bytes(int S, int KT, int W = 55) {
+  const int wstride = (32 * KT + 2 * (W / 2) + 2) & ~1;
+  return sizeof(double) * (size_t)((FAST_TPB / 32) * wstride + (size_t)S * (W + 1));
 }
+// window lengths the split form is instantiated for, and the samples per thread its register window allows
+bool split_window_supported(int W) { return W == 21 || W == 33 || W == 55 || W == 101; }
+static int split_max_kt(int W) { return W == 101 ? 2 : 4; }
 static size_t epi_smem_bytes(int G, int S, int arows, int SPT) {
   return sizeof(double) * ((size_t)(3 * ((G + 1) & ~1) + MAXH + BFL_EXPHI_SIZE) + (size_t)arows * SPT * EPI_TPB) +
          sizeof(int) * (size_t)(2 * S) + sizeof(short) * (size_t)(G + 8);
@@ -1500,7 +1505,7 @@ static int epi_arows(const PlanView& pv) {
 bool fast_split_fits(const PlanView& pv) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_SPLIT"); off = (e && atoi(e)) ? 1 : 0; }
-  return !off && pv.sep_ok && pv.W == 55 && corr_smem_bytes(pv.S, 4) <= 70 * 1024 && pv.wsep_ok &&
+  return !off && pv.sep_ok && split_window_supported(pv.W) && corr_smem_bytes(pv.S, 4, pv.W) <= 70 * 1024 && pv.wsep_ok &&
          epi_smem_bytes(pv.G, pv.S, epi_arows(pv), BFL_EPI_SPT) <= 50 * 1024 * BFL_EPI_SPT;   // wsep_ok: templates grouped by B shape
 }
 
@@ -1543,21 +1548,26 @@ cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratc
   c.B = sv.B; c.tiles_per_curve = (int)((nk + 32 * KT - 1) / (32 * KT));
   c.total_wtiles = (int64_t)c.tiles_per_curve * sv.B; c.tile_counter = sc.split_counters; c.done_counter = sc.split_counters + 2;
   c.shapes = pv.shapes; c.S = pv.S; c.WP = pv.WP; c.Y = sc.Y;
-  const size_t smem1 = corr_smem_bytes(pv.S, KT);
+  const size_t smem1 = corr_smem_bytes(pv.S, KT, pv.W);
   cudaError_t e;
-#define BFL_CORR(KT_)                                                                                       \
+#define BFL_CORR(W_, KT_)                                                                                   \
   do {                                                                                                      \
-    e = cudaFuncSetAttribute(k_corr_shapes<KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);  \
+    e = cudaFuncSetAttribute(k_corr_shapes<W_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1); \
     if (e != cudaSuccess) return e;                                                                         \
     int occ = 1;                                                                                            \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_corr_shapes<KT_>, FAST_TPB, smem1);           \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_corr_shapes<W_, KT_>, FAST_TPB, smem1);       \
     if (e != cudaSuccess) return e;                                                                         \
     int64_t gx = (int64_t)sms * (occ < 1 ? 1 : occ);                                                        \
     const int64_t need = (c.total_wtiles + FAST_TPB / 32 - 1) / (FAST_TPB / 32);                            \
     if (gx > need) gx = need;                                                                               \
-    k_corr_shapes<KT_><<<(unsigned)(gx < 1 ? 1 : gx), FAST_TPB, smem1, s>>>(c);                             \
+    k_corr_shapes<W_, KT_><<<(unsigned)(gx < 1 ? 1 : gx), FAST_TPB, smem1, s>>>(c);                         \
   } while (0)
-  if (KT == 4) BFL_CORR(4); else if (KT == 2) BFL_CORR(2); else BFL_CORR(1);
+#define BFL_CORR_W(W_) do { if (KT == 4) BFL_CORR(W_, 4); else if (KT == 2) BFL_CORR(W_, 2); else BFL_CORR(W_, 1); } while (0)
+  if (pv.W == 21) BFL_CORR_W(21);
+  else if (pv.W == 33) BFL_CORR_W(33);
+  else if (pv.W == 101) { if (KT >= 2) BFL_CORR(101, 2); else BFL_CORR(101, 1); }
+  else BFL_CORR_W(55);
+#undef BFL_CORR_W
 #undef BFL_CORR
   st->launches++;
   e = cudaGetLastError();
@@ -1632,8 +1642,9 @@ int pick_gchunk(int G, int W, int64_t total_samples, int sm_count, int* KT_out) 
   const int64_t want = 2LL * sm_count;   // at least two CTAs per SM when the problem allows
   int KT = 4;
   if (const char* e = getenv("BFL_KT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) KT = v; }
-  if (W != 55) KT = 1;
+  if (!split_window_supported(W)) KT = 1;
   else {
+    KT = std::min(KT, split_max_kt(W));
     while (KT > 1 && (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT) < want) KT >>= 1;
   }
   const int64_t tiles = (total_samples + FAST_TPB * KT - 1) / (FAST_TPB * KT);   // CTA-sized groups of warp tiles
@@ -1719,13 +1730,13 @@ static cudaError_t launch_fast_impl(FastArgs& a, int KT, bool sep, cudaStream_t 
 bool fast_sep_fits(const PlanView& pv, int KT) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_SEP"); off = (e && atoi(e)) ? 1 : 0; }
-  return !off && pv.sep_ok && KT <= 4 && fast_sep_smem_bytes(pv.W, pv.G, pv.S, KT, sep_arows(pv)) <= 220 * 1024;
+  return !off && pv.sep_ok && pv.W == 55 && KT <= 4 && fast_sep_smem_bytes(pv.W, pv.G, pv.S, KT, sep_arows(pv)) <= 220 * 1024;
 }
 static bool use_sep(const PlanView& pv, const Scratch& sc, int KT) { return sc.NC == 1 && fast_sep_fits(pv, KT); }
 
 static int kt_for(const PlanView& pv, const SeriesView& sv, const Scratch& sc) {
-  (void)pv; (void)sv;
-  return sc.KT;
+  (void)sv;
+  return pv.W == 55 ? sc.KT : 1;     // the single-kernel path has a register window for W = 55 only
 }
 
 cudaError_t launch_window_fast_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,
@@ -2813,7 +2824,7 @@ static int wsep_arows(const PlanView& pv) {
 bool wsep_fits(const PlanView& pv) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_WSEP"); off = (e && atoi(e)) ? 1 : 0; }
-  return !off && pv.wsep_ok && pv.G > 0 && pv.P >= 1 && pv.P <= 6 && wsep_arows(pv) >= WSEP_GT;
+  return !off && pv.wsep_ok && pv.W <= 55 && pv.G > 0 && pv.P >= 1 && pv.P <= 6 && wsep_arows(pv) >= WSEP_GT;
 }
 
 cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scratch& sc, cudaStream_t s,

@@ -170,6 +170,7 @@ cudaError_t launch_sweep_score(const double* d_lnO, int B, int64_t nk, int h, co
                                cudaStream_t s, LaunchStats* st);
 
 bool fast_split_fits(const PlanView& pv);
+bool split_window_supported(int W);
 bool epi2_fits(const PlanView& pv);
 size_t epi2_plan_block_bytes(const PlanView& pv);
 cudaError_t launch_epilogue2_prepare(const PlanView& pv, int noisepoly, void* d_block, cudaStream_t s, LaunchStats* st);

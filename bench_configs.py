@@ -251,9 +251,32 @@ def config6(B=512):
             "units_per_s_window_kernels": units / (ms * 1e-3), "parity_sample": "2 curves", "parity_max_scaled_err": max(errs)}
 
 
+def config7(B=1024):
+    """extra (not a BASELINE config): the config-3 batch with OTHER window lengths -- the split form is instantiated
+    for bglen 21, 33, 55 and 101 (the lengths the reference's scripts use), anything else takes the single-kernel path"""
+    N = 4400
+    cts, clc, _ = simulate_batch(B, N, seed=100)
+    out = {"config": "7 (extra)", "what": config7.__doc__, "B": B, "N": N, "by_bglen": {}}
+    for bglen in (21, 33, 55, 101, 35):
+        det = bf.OddsRatioDetector(bf.Lightcurve(cts=cts, clc=clc[0]), bglen=bglen)
+        ctx = det.plan().ctx
+        sk = np.ones(B)
+        det.oddsratio_batch(clc, sk=sk)
+        ctx.set_timing(True)
+        ctx.window_time()
+        lnO = det.oddsratio_batch(clc, sk=sk)
+        ms, nl = ctx.window_time()
+        ctx.set_timing(False)
+        units = B * (N - 2 * (bglen // 2)) * det.ngrid_eval
+        ref, _ = orc.oddsratio(clc[1], np.zeros(N), cts, sk=1.0, bglen=bglen)
+        out["by_bglen"][str(bglen)] = {"window_kernels_ms": ms, "launches": nl, "units_per_s_window_kernels": units / (ms * 1e-3),
+                                       "shapes": det.plan().shape_count, "parity_max_scaled_err_curve1": scaled_err(lnO[1], ref)}
+    return out
+
+
 def main():
-    which = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5, 6]
-    fns = {1: config1, 2: config2, 4: config4, 5: config5, 6: config6}
+    which = [int(a) for a in sys.argv[1:]] or [1, 2, 4, 5, 6, 7]
+    fns = {1: config1, 2: config2, 4: config4, 5: config5, 6: config6, 7: config7}
     for w in which:
         if w == 3:
             print(json.dumps({"config": 3, "what": "see bench.py (the contract benchmark runs this configuration)"}))

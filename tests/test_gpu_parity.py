@@ -1043,3 +1043,22 @@ def test_whole_series_background_vs_reference(tag, monkeypatch):
     assert np.array_equal(np.isfinite(lnO), fin)
     err = np.abs(np.array(lnO)[fin] - np.array(want)[fin]) / np.maximum(1.0, np.abs(np.array(want)[fin]))
     assert err.max() <= TOL, err.max()
+
+
+@pytest.mark.parametrize("bglen,bgorder", [(21, 2), (33, 4), (101, 4)])
+def test_split_form_other_window_lengths_vs_oracle(bglen, bgorder):
+    """The two-kernel split form (k_corr_shapes<W, KT> + k_epilogue2) is instantiated for W = 21, 33, 55, 101: a batch
+    large enough to take it, against the oracle on two curves and against the single-kernel path curve by curve."""
+    from bayesflare_b200.synthetic import simulate_batch
+    B, N = 192, 1500
+    cts, clc, _ = simulate_batch(B, N, seed=31)
+    det = bf.OddsRatioDetector(_lc(cts, clc[0]), bglen=bglen, bgorder=bgorder)
+    h = bglen // 2
+    sk = np.full(B, 1.07)
+    lnO = det.oddsratio_batch(clc, sk=sk)
+    assert lnO.shape == (B, N - 2 * h) and np.all(np.isfinite(lnO))
+    for b in (0, B - 1):
+        ref, _ = orc.oddsratio(clc[b], np.zeros(N), cts, sk=1.07, bglen=bglen, bgorder=bgorder)
+        assert_logodds_close(lnO[b], ref, TOL, "split form W=%d curve %d" % (bglen, b))
+        single = det.plan().detector_odds(clc[b], None, 1.07, k0=h, k1=N - h)
+        np.testing.assert_allclose(lnO[b], single, rtol=0, atol=5e-11)
