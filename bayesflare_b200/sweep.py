@@ -128,6 +128,10 @@ def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, sn
                                        d_clc.data_ptr(), d_truth.data_ptr())
                 ctx.noise_sigma_dev(spec_script, d_clc.data_ptr(), nb, N, d_skb.data_ptr())
                 ctx.sweep_inject_dev(kind, nb, N, dt, d_skb.data_ptr(), d_truth.data_ptr(), d_clc.data_ptr())
+                if kind == 2:
+                    # script :616-623: with --injtransit EVERY above-threshold segment of the flare detector is a false
+                    # positive ("a transit or impulse was detected, so anything is a false positive"): no injection index
+                    d_truth[:nb, 0] = -1.0
             else:
                 ctx.sweep_simulate_dev(seed, first, nb, N, h, dt, 1.0, sinusoid_amp, 0., snr_max, 1,
                                        d_clc.data_ptr(), d_truth.data_ptr())
@@ -153,7 +157,10 @@ def detection_efficiency(nreal, N=1639, dt=DT_LONG, threshold=16.5, nbins=50, sn
             lnO = det.oddsratio_batch(clc)                 # [nb, N - 2h], noise sigma estimated on the device
             t_gpu += time.perf_counter() - t0
             units += nb * (N - 2 * h) * det.ngrid_eval
-            inj, dete, fa, _ = score_host(lnO, truth["idx"] - h, truth["snr"], threshold, edges)
+            inj_idx = truth["idx"] - h
+            if recipe == "script" and inject == "transit":
+                inj_idx = np.full(nb, -1)                   # script :616-623: every segment is a false positive
+            inj, dete, fa, _ = score_host(lnO, inj_idx, truth["snr"], threshold, edges)
             injected += inj
             detected += dete
             false_alarms += fa
@@ -203,7 +210,7 @@ def main():
                "recipe": "script" if args.injtransit else args.recipe, "injection": "transit" if args.injtransit else "flare", "wall_s": wall, "t_detector_s_rank0": res["t_detector_s"],
                "t_simulate_s_rank0": res["t_simulate_s"], "units": res["units"],
                "units_per_s_detector": res["units"] / world / max(res["t_detector_s"], 1e-9) * world,
-               "false_alarms": res["false_alarms"],
+               "false_alarms": res["false_alarms"], "false_alarms_per_realisation": res["false_alarms"] / max(res["realisations"], 1),
                "efficiency_by_snr_decade": [float(res["detected"][i:i + 10].sum() / max(res["injected"][i:i + 10].sum(), 1))
                                             for i in range(0, 50, 10)],
                "injected": res["injected"].tolist(), "detected": res["detected"].tolist()}

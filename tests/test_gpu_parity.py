@@ -977,18 +977,16 @@ def test_sweep_script_recipe_injection_on_device_vs_host():
             assert abs(sk_dev[b] - sk_host) <= 1e-12 * sk_host
             want = base[b] + inj * fac
             np.testing.assert_allclose(got[b], want, rtol=0, atol=1e-11 * max(1.0, np.max(np.abs(want))))
+    # --injtransit (script :616-623): every above-threshold segment of the flare detector is a false positive
     whole = detection_efficiency(2048, N=N, seed=6, batch=1024, device_sim=True, recipe="script", inject="transit", sinusoid_amp=2.0)
-    assert whole["injected"].sum() == 2048
+    assert whole["injected"].sum() == 0 and whole["detected"].sum() == 0 and whole["false_alarms"] > 0
     parts = [detection_efficiency(2048, N=N, seed=6, batch=512, rank=r, world=2, device_sim=True, recipe="script",
                                   inject="transit", sinusoid_amp=2.0) for r in range(2)]
-    np.testing.assert_array_equal(sum(p["injected"] for p in parts), whole["injected"])
-    np.testing.assert_array_equal(sum(p["detected"] for p in parts), whole["detected"])
-    # the flare detector sees transits mostly at ingress / egress: efficiencies are whatever they are, but device
-    # and host simulations of the same recipe must agree statistically (different random streams)
+    assert sum(p["false_alarms"] for p in parts) == whole["false_alarms"]
+    # device and host simulations of the same recipe must agree statistically (different random streams)
     host = detection_efficiency(512, N=N, seed=6, batch=512, recipe="script", inject="transit", sinusoid_amp=2.0)
-    fd = whole["detected"].sum() / whole["injected"].sum()
-    fh = host["detected"].sum() / host["injected"].sum()
-    assert abs(fd - fh) < 0.08, (fd, fh)
+    fd, fh = whole["false_alarms"] / 2048.0, host["false_alarms"] / 512.0
+    assert abs(fd - fh) < 0.15 * max(fd, fh), (fd, fh)
     fl_d = detection_efficiency(1024, N=N, seed=8, batch=1024, device_sim=True, recipe="script", inject="flare")
     fl_h = detection_efficiency(512, N=N, seed=8, batch=512, recipe="script", inject="flare")
     ed = fl_d["detected"][20:].sum() / fl_d["injected"][20:].sum()
