@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -161,6 +162,7 @@ class Context:
         check(self.lib.bfl_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = int(device)          # -1: the device that was current at creation
+        self._plans = weakref.WeakSet()    # plans hold a pointer into this context: closed before it
 
     def sync(self):
         check(self.lib.bfl_ctx_sync(self.handle))
@@ -213,6 +215,8 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
+            for p in list(getattr(self, "_plans", ())):     # bfl_plan_destroy synchronises the context's stream
+                p.close()
             self.lib.bfl_ctx_destroy(self.handle)
             self.handle = None
 
@@ -272,6 +276,7 @@ class Plan:
         check(self.lib.bfl_plan_create(ctx.handle, self.bglen, self.npoly, ptr(bg), ptr(keep[1]), arr, self.nhyp,
                                        C.byref(hnd)))
         self.handle = hnd
+        ctx._plans.add(self)
 
     @property
     def shape_count(self):

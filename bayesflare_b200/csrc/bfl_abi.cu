@@ -733,13 +733,33 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
       CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       c->pipe_ev.push_back(ev);
     }
-    // scratch sized once for the largest sub-batch so nothing is reallocated mid-pipeline
-    if (sk) CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
-    CK(cudaEventRecord(c->pipe_ev[2 * nsub], s));
-    CK(cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * nsub], 0));   // previous users of the input buffers are done
     std::vector<int> lo(nsub + 1);
     if (nsub == 4) { lo[0] = 0; lo[1] = B / 8; lo[2] = B / 2; lo[3] = B - B / 8; lo[4] = B; }
     else for (int j = 0; j <= nsub; j++) lo[j] = (int)((int64_t)B * j / nsub);
+    // scratch is sized ONCE, for the largest sub-batch, before anything is in flight: growing a buffer
+    // mid-pipeline would synchronise, free and reallocate under the copy streams
+    {
+      int bmax = 0;
+      for (int j = 0; j < nsub; j++) bmax = std::max(bmax, lo[j + 1] - lo[j]);
+      SeriesView svmax{(const double*)d_clc, cle ? (const double*)d_cle : nullptr, (const double*)d_sk, bmax, N, 0, N, k0, k1, cv ? 1 : 0};
+      Scratch scmax{};
+      const bool edges = range_has_edges(p->pv, svmax);
+      if ((rc = check_series(p->pv, svmax))) return rc;
+      if ((rc = setup_scratch(c, p->pv, svmax, !cv || edges, false, false, scmax, !cv && wsep_fits(p->pv)))) return rc;
+      if (!sk && noise) {
+        void* tmp;
+        if (noise->bglen && (rc = c->get("sg_resid", sizeof(double) * (size_t)bmax * N, &tmp))) return rc;
+        if (noise->method == 0 && (rc = c->get("fft_out", sizeof(double2) * (size_t)bmax * (N / 2 + 1), &tmp))) return rc;
+      }
+    }
+    // an error below leaves asynchronous copies to / from CALLER memory in flight: drain all three streams first
+    auto bail = [&](int code) {
+      cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(s); cudaStreamSynchronize(c->s_out);
+      return code;
+    };
+    if (sk) CK(cudaMemcpyAsync(d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(c->pipe_ev[2 * nsub], s));
+    CK(cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * nsub], 0));   // previous users of the input buffers are done
     for (int j = 0; j < nsub; j++) {
       const size_t off = (size_t)lo[j] * N, cnt = (size_t)(lo[j + 1] - lo[j]) * N;
       CK(cudaMemcpyAsync((double*)d_clc + off, clc + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, c->s_in));
@@ -750,10 +770,10 @@ int bfl_detector_odds(bfl_ctx* c, bfl_plan* p, int noisepoly, const double* clc,
       const int Bj = lo[j + 1] - lo[j];
       const size_t off = (size_t)lo[j] * N, ooff = (size_t)lo[j] * nk;
       CK(cudaStreamWaitEvent(s, c->pipe_ev[j], 0));
-      if (!sk && (rc = noise_run(c, noise, (const double*)d_clc + off, Bj, N, (double*)d_sk + lo[j]))) return rc;
+      if (!sk && (rc = noise_run(c, noise, (const double*)d_clc + off, Bj, N, (double*)d_sk + lo[j]))) return bail(rc);
       SeriesView sv{(const double*)d_clc + off, cle ? (const double*)d_cle + off : nullptr, (const double*)d_sk + lo[j],
                     Bj, N, 0, N, k0, k1, cv ? 1 : 0};
-      if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO + ooff, nullptr))) return rc;
+      if ((rc = detector_run(c, p, noisepoly, sv, (double*)d_lnO + ooff, nullptr))) return bail(rc);
       CK(cudaEventRecord(c->pipe_ev[nsub + j], s));
       CK(cudaStreamWaitEvent(c->s_out, c->pipe_ev[nsub + j], 0));
       CK(cudaMemcpyAsync(out_lnO + ooff, (double*)d_lnO + ooff, sizeof(double) * (size_t)Bj * nk, cudaMemcpyDeviceToHost,
@@ -1005,7 +1025,7 @@ int bfl_sweep_simulate_dev(bfl_ctx* c, uint64_t seed, int64_t first, int32_t B, 
 }
 
 int bfl_sweep_inject_dev(bfl_ctx* c, int32_t kind, int32_t B, int32_t N, double dt, const double* d_sk,
-                         const double* d_truth, double* d_clc) {
+                         double* d_truth, double* d_clc) {
   if (!c || !d_sk || !d_truth || !d_clc) return fail(BFL_ERR_ARG, "null argument to bfl_sweep_inject_dev");
   if ((kind != 1 && kind != 2) || B < 1 || N < 2 || !(dt > 0.0)) return fail(BFL_ERR_ARG, "bad argument to bfl_sweep_inject_dev");
   CK(cudaSetDevice(c->device));

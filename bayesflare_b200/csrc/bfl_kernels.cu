@@ -395,6 +395,16 @@ cudaError_t launch_prep(const SeriesView& sv, Scratch& sc, bool need_general, cu
   return cudaGetLastError();
 }
 
+// SM count of the CURRENT device (a process may drive several devices of different sizes)
+static int sm_count_current() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!cache[dev]) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cache[dev];
+}
+
 // ======================================================================================
 // FAST path
 // ======================================================================================
@@ -1539,8 +1549,7 @@ cudaError_t launch_epilogue2_prepare(const PlanView& pv, int noisepoly, void* d_
 // mode: 0 = partial sums per hypothesis (sc.part, NC = sub = 1 layout), 2 = log odds
 cudaError_t launch_window_split(const PlanView& pv, const SeriesView& sv, Scratch& sc, int mode, int noisepoly,
                                 double* d_lnO, cudaStream_t s, LaunchStats* st) {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int sms = sm_count_current();
   const int64_t nk = sv.k1 - sv.k0;
   const int KT = sc.KT;
   CorrArgs c;
@@ -1688,12 +1697,7 @@ static void fill_fast_args(FastArgs& a, const PlanView& pv, const SeriesView& sv
 template <int MODE>
 static cudaError_t launch_fast_impl(FastArgs& a, int KT, bool sep, cudaStream_t s, LaunchStats* st) {
   const size_t smem = sep ? fast_sep_smem_bytes(a.W, a.G, a.S, KT, a.arows) : fast_smem_bytes(a.W, a.gchunk, KT);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_count_current();
   cudaError_t e = cudaSuccess;
   // persistent grid: as many CTAs as the device holds at once (or fewer if there is less work)
 #define BFL_LAUNCH(WT_, KT_, SEP_)                                                                        \
@@ -2845,12 +2849,7 @@ cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scr
   a.logdetG = pv.logdetG;
   a.part = sc.part; a.bgabs = sc.bgabs;
   const size_t smem = wsep_smem(pv.P, pv.W, pv.G, pv.S, a.arows);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = sm_count_current();
   dim3 grid((unsigned)std::min<int64_t>(a.total_tiles, sms));   // persistent: one CTA per SM (shared-memory bound)
   cudaError_t e = cudaSuccess;
 #define BFL_WS(P_)                                                                                              \
@@ -3728,7 +3727,8 @@ cudaError_t launch_sweep_simulate(unsigned long long seed, long long first, int 
 // kind 1: Flare (p1, p2) = (tau_gauss, tau_exp), models/model.py:197-252; kind 2: Transit (p1, p2) = (sigma_g, tau_f),
 // models/model.py:387-436 (amp = 1: -1 inside |t - t0| <= tau_f, Gaussian wings outside).
 __global__ void __launch_bounds__(256) k_sweep_inject(int kind, int N, double dt, const double* __restrict__ sk,
-                                                      const double* __restrict__ truth, double* __restrict__ clc) {
+                                                      const double* truth, double* __restrict__ clc, int clear_idx,
+                                                      double* truth_rw) {
   const int b = blockIdx.x, tid = threadIdx.x;
   __shared__ double red[256];
   const double* t = truth + (size_t)b * 4;
@@ -3758,11 +3758,17 @@ __global__ void __launch_bounds__(256) k_sweep_inject(int kind, int N, double dt
   const double scale = snr / injsnr;
   double* x = clc + (size_t)b * N;
   for (int i = tid; i < N; i += 256) x[i] += model(i) * scale;
+  // script :616-623: with a transit injected, EVERY above-threshold segment of the flare detector is a false positive
+  // ("a transit or impulse was detected, so anything is a false positive"): the scoring kernel gets no injection index
+  if (kind == 2 && clear_idx) {
+    __syncthreads();
+    if (tid == 0) truth_rw[(size_t)b * 4] = -1.0;
+  }
 }
 
-cudaError_t launch_sweep_inject(int kind, int B, int N, double dt, const double* d_sk, const double* d_truth, double* d_clc,
+cudaError_t launch_sweep_inject(int kind, int B, int N, double dt, const double* d_sk, double* d_truth, double* d_clc,
                                 cudaStream_t s, LaunchStats* st) {
-  k_sweep_inject<<<B, 256, 0, s>>>(kind, N, dt, d_sk, d_truth, d_clc);
+  k_sweep_inject<<<B, 256, 0, s>>>(kind, N, dt, d_sk, d_truth, d_clc, 1, d_truth);
   st->launches++;
   return cudaGetLastError();
 }

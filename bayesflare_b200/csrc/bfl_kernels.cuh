@@ -163,7 +163,7 @@ cudaError_t launch_fp64_probe(double* d_sink, int iters, int blocks, cudaStream_
 cudaError_t launch_sweep_simulate(unsigned long long seed, long long first, int B, int N, int H, double dt, double nstd,
                                   double sinusoid_amp, double snr_lo, double snr_hi, int inject, double* d_clc,
                                   double* d_truth, cudaStream_t s, LaunchStats* st);
-cudaError_t launch_sweep_inject(int kind, int B, int N, double dt, const double* d_sk, const double* d_truth, double* d_clc,
+cudaError_t launch_sweep_inject(int kind, int B, int N, double dt, const double* d_sk, double* d_truth, double* d_clc,
                                 cudaStream_t s, LaunchStats* st);
 cudaError_t launch_sweep_score(const double* d_lnO, int B, int64_t nk, int h, const double* d_truth, double thresh,
                                int nbins, double snr_max, int64_t* d_injected, int64_t* d_detected, int64_t* d_counters,

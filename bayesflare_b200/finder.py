@@ -154,7 +154,11 @@ class OddsRatioDetector:
         cts = np.asarray(cts, dtype=float)
         quick = (self.bglen, self.bgorder, len(cts), float(cts[0]), float(cts[1]), float(cts[len(cts) // 2]),
                  float(cts[-1]), self.noisepoly, self.noiseimpulse, self.noiseimpulsepositive, self.noiseexpdecay,
-                 self.noiseexpdecaywithreverse, self.noisestep)
+                 self.noiseexpdecaywithreverse, self.noisestep,
+                 # the reference re-reads these dictionaries on every oddsratio(): direct assignment or mutation
+                 # of them must not leave stale templates behind
+                 repr(sorted(self.flareparams.items())), repr(sorted(self.noiseimpulseparams.items())),
+                 repr(sorted(self.noiseexpdecayparams.items())), repr(sorted(self.noisestepparams.items())))
         if self._plan is not None and self._plan_key is not None and quick == getattr(self, "_plan_quick", None):
             return self._plan          # setters reset _plan_key, so an unchanged configuration lands here
         if self.bglen is None or self.nsinusoids != 0:
@@ -310,9 +314,14 @@ class OddsRatioDetector:
     def thresholder(self, lnO, thresh, expand=0, returnmax=True):
         """Regions where ``lnO > thresh``, optionally expanded and merged, with the maximum of each
         (find.py:915-1019).  The scan, merge and per-region argmax run through ``bfl_threshold``."""
-        segs, mv, mi = _lib.threshold(_lib.default_context(self.device), np.asarray(lnO, dtype=float), thresh, expand)
-        if expand > 0 and len(segs) == 1:
-            flarelist = [[int(segs[0, 0]), int(segs[0, 1])]]     # the reference returns a list here (find.py:961)
+        lnOa = np.asarray(lnO, dtype=float)
+        segs, mv, mi = _lib.threshold(_lib.default_context(self.device), lnOa, thresh, expand)
+        above = lnOa > thresh
+        nraw = int(np.count_nonzero(above[1:] & ~above[:-1]) + (1 if len(above) and above[0] else 0))
+        if expand > 0 and nraw == 1:
+            # the reference returns a list (not a tuple) when exactly ONE region was found before expansion
+            # (find.py:954-965); several regions that merge into one stay a tuple
+            flarelist = [[int(segs[0, 0]), int(segs[0, 1])]]
         else:
             flarelist = [(int(a), int(b)) for a, b in segs]
         if returnmax:

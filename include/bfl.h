@@ -212,7 +212,8 @@ int bfl_pipe_destroy(bfl_pipe* pipe);
  *   d_clc dev [B][N] out; d_truth dev [B][4] out: injection index (or -1), snr, then (tau_gauss, tau_exp) or
  *   (sigma_g, tau_f).
  * bfl_sweep_inject_dev: kind 1 = Flare.model, 2 = Transit.model at amplitude 1 on the whole series;
- *   d_clc[b] += model * snr / ((1 / d_sk[b]) sqrt(sum model^2)).
+ *   d_clc[b] += model * snr / ((1 / d_sk[b]) sqrt(sum model^2)).  For a transit the injection index in d_truth is
+ *   then set to -1: the script counts EVERY segment of the flare detector as a false positive there (:616-623).
  * bfl_sweep_score_dev: above-threshold runs of d_lnO[B][nk] (edge-trimmed by halfwin) expanded by +-2 samples
  *   and merged (script :521-580); the region holding the injection is a detection, every other one a false
  *   positive (:586-612).  ACCUMULATES (arrays not cleared): d_injected / d_detected [nbins] histograms over
@@ -222,7 +223,7 @@ int bfl_sweep_simulate_dev(bfl_ctx* ctx, uint64_t seed, int64_t first, int32_t B
                            double nstd, double sinusoid_amp, double snr_lo, double snr_hi, int32_t inject, double* d_clc,
                            double* d_truth);
 int bfl_sweep_inject_dev(bfl_ctx* ctx, int32_t kind, int32_t B, int32_t N, double dt, const double* d_sk,
-                         const double* d_truth, double* d_clc);
+                         double* d_truth, double* d_clc);
 int bfl_sweep_score_dev(bfl_ctx* ctx, const double* d_lnO, int32_t B, int64_t nk, int32_t halfwin, const double* d_truth,
                         double thresh, int32_t nbins, double snr_max, int64_t* d_injected, int64_t* d_detected,
                         int64_t* d_counters);
