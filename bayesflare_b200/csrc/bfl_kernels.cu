@@ -3351,18 +3351,19 @@ cudaError_t launch_region_max(const double* d_lnO, const int64_t* d_segs, int ns
 // noise.py:236-240) is staged in shared memory once, every thread then takes its W taps from there in the
 // reference's order (np.convolve(m[::-1], y, 'valid')), so the result is bit-identical to a thread-per-sample
 // loop over global memory -- which took 29 us for 128 curves, a seventh of a whole detector step.
-constexpr int SG_TPB = 256;
+constexpr int SG_TPB = 128, SG_KT = 4;       // 128 threads x 4 consecutive samples each = 512 samples per CTA
 __global__ void __launch_bounds__(SG_TPB) k_sg_resid(const double* __restrict__ y, int64_t N, int B,
                                                      const double* __restrict__ m, int W, double* __restrict__ resid) {
   extern __shared__ double smem[];
-  double* sv = smem;                   // [SG_TPB + W - 1] padded series, positions i0 .. i0 + SG_TPB + W - 2
-  double* sm = smem + SG_TPB + W - 1;  // [W] filter taps
+  constexpr int TS = SG_TPB * SG_KT;
+  double* sv = smem;                   // [TS + W - 1] padded series, positions i0 .. i0 + TS + W - 2
+  double* sm = smem + TS + W - 1;      // [W] filter taps
   const int b = blockIdx.y;
-  const int64_t i0 = (int64_t)blockIdx.x * SG_TPB;
+  const int64_t i0 = (int64_t)blockIdx.x * TS;
   const double* yy = y + (size_t)b * N;
   const int h = (W - 1) / 2;
   const double y0 = yy[0], yl = yy[N - 1];
-  for (int e = threadIdx.x; e < SG_TPB + W - 1; e += SG_TPB) {
+  for (int e = threadIdx.x; e < TS + W - 1; e += SG_TPB) {
     const int64_t t = i0 + e;          // index into the padded series
     double v = 0.0;
     if (t < h) v = y0 - fabs(yy[h - t] - y0);
@@ -3372,11 +3373,28 @@ __global__ void __launch_bounds__(SG_TPB) k_sg_resid(const double* __restrict__ 
   }
   for (int j = threadIdx.x; j < W; j += SG_TPB) sm[j] = m[j];
   __syncthreads();
-  const int64_t i = i0 + threadIdx.x;
-  if (i >= N) return;
-  double fit = 0.0;
-  for (int j = 0; j < W; j++) fit = fma(sm[j], sv[threadIdx.x + j], fit);
-  resid[(size_t)b * N + i] = sv[threadIdx.x + h] - fit;
+  // SG_KT consecutive samples per thread: every padded value is read once per thread instead of once per sample,
+  // every tap once per SG_KT samples; each sample's sum still runs over the taps in the reference's order
+  const int base = threadIdx.x * SG_KT;
+  double fit[SG_KT];
+#pragma unroll
+  for (int q = 0; q < SG_KT; q++) fit[q] = 0.0;
+  double win[SG_KT];
+#pragma unroll
+  for (int q = 0; q < SG_KT - 1; q++) win[q + 1] = sv[base + q];
+  for (int j = 0; j < W; j++) {
+#pragma unroll
+    for (int q = 0; q < SG_KT - 1; q++) win[q] = win[q + 1];
+    win[SG_KT - 1] = sv[base + j + SG_KT - 1];
+    const double c = sm[j];
+#pragma unroll
+    for (int q = 0; q < SG_KT; q++) fit[q] = fma(c, win[q], fit[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < SG_KT; q++) {
+    const int64_t i = i0 + base + q;
+    if (i < N) resid[(size_t)b * N + i] = sv[base + q + h] - fit[q];
+  }
 }
 
 // 'powerspectrum' estimator: sigma^2 = mean of the upper `estfrac` of the one-sided periodogram
@@ -3506,8 +3524,9 @@ __global__ void __launch_bounds__(128) k_tv_finish(const int* __restrict__ count
 
 cudaError_t launch_sg_resid(const double* d_y, int64_t N, int B, const double* d_m, int W, double* d_resid,
                             cudaStream_t s, LaunchStats* st) {
-  const dim3 grid((unsigned)((N + SG_TPB - 1) / SG_TPB), (unsigned)B);
-  const size_t smem = sizeof(double) * (size_t)(SG_TPB + 2 * W - 1);
+  const int ts = SG_TPB * SG_KT;
+  const dim3 grid((unsigned)((N + ts - 1) / ts), (unsigned)B);
+  const size_t smem = sizeof(double) * (size_t)(ts + 2 * W - 1);
   k_sg_resid<<<grid, SG_TPB, smem, s>>>(d_y, N, B, d_m, W, d_resid);
   st->launches++;
   return cudaGetLastError();
