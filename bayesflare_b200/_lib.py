@@ -108,6 +108,7 @@ SIGNATURES = {
                                   C.c_void_p, _i64p]),
     "bfl_pipe_wait": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "bfl_pipe_launch_count": (C.c_int64, [C.c_void_p]),
+    "bfl_pipe_graph_count": (C.c_int32, [C.c_void_p]),
     "bfl_pipe_destroy": (C.c_int, [C.c_void_p]),
     "bfl_threshold": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_double, C.c_int32, _i64p, _dp, _i64p, C.c_int32,
                                 C.POINTER(C.c_int32)]),
@@ -386,6 +387,11 @@ class Pipe:
     @property
     def launches(self):
         return int(self.lib.bfl_pipe_launch_count(self.handle))
+
+    @property
+    def graphs(self):
+        """CUDA graphs instantiated for recurring (slot, host buffers) combinations."""
+        return int(self.lib.bfl_pipe_graph_count(self.handle))
 
     def close(self):
         if getattr(self, "handle", None):

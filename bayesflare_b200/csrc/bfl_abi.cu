@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,8 @@ struct bfl_ctx {
   LaunchStats stats;
   bool timing = false;
   void* counters_zeroed = nullptr;                          // the tile-counter allocation that has been cleared
+  std::vector<double> sg_cached;                            // Savitzky-Golay taps currently on the device ...
+  void* sg_cached_dev = nullptr;                            // ... and the buffer that holds them
   cudaStream_t s_in = nullptr, s_out = nullptr;           // copy streams of the pipelined host entry point
   std::vector<cudaEvent_t> pipe_ev;                        // cached events for it
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev;   // pending (start, stop) pairs of the window kernel
@@ -636,7 +639,14 @@ static int noise_run(bfl_ctx* c, const bfl_noise_spec* spec, const double* d_clc
     void* d_m;
     if ((rc = c->get("sg_coef", sizeof(double) * MAXW, &d_m))) return rc;
     if ((rc = c->get("sg_resid", sizeof(double) * (size_t)B * N, &ptr))) return rc;
-    CK(cudaMemcpyAsync(d_m, spec->sgcoef, sizeof(double) * (size_t)spec->bglen, cudaMemcpyHostToDevice, s));
+    // the filter taps are uploaded only when they change (and never during a stream capture: the source is pageable)
+    if (c->sg_cached.size() != (size_t)spec->bglen || c->sg_cached_dev != d_m ||
+        std::memcmp(c->sg_cached.data(), spec->sgcoef, sizeof(double) * (size_t)spec->bglen) != 0) {
+      c->sg_cached.assign(spec->sgcoef, spec->sgcoef + spec->bglen);
+      c->sg_cached_dev = d_m;
+      CK(cudaMemcpyAsync(d_m, c->sg_cached.data(), sizeof(double) * (size_t)spec->bglen, cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+    }
     CK(launch_sg_resid(d_clc, N, B, (const double*)d_m, spec->bglen, (double*)ptr, s, &c->stats));
     d_res = (const double*)ptr;
   }
@@ -823,11 +833,26 @@ struct bfl_pipe {
   };
   std::vector<Slot> slots;
   int64_t submitted = 0;
+  // A job's whole enqueue sequence (copies, ~10 kernels, copies) as ONE CUDA graph per (slot, host buffers, mode):
+  // callers cycle through a few page-locked buffers, and on a box with 8 ranks the ~15 runtime calls per job were
+  // what kept the GPUs waiting.  Captured the second time a key is seen on a warm slot.
+  struct GraphKey {
+    int slot; const void *clc, *sk, *lnO, *reg, *cnt, *osk; uint64_t thresh_bits;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(slot, clc, sk, lnO, reg, cnt, osk, thresh_bits) <
+             std::tie(o.slot, o.clc, o.sk, o.lnO, o.reg, o.cnt, o.osk, o.thresh_bits);
+    }
+  };
+  struct GraphVal { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+  std::map<GraphKey, GraphVal> graphs;
+  bool use_graphs = true;
 };
 
 int bfl_pipe_destroy(bfl_pipe* p) {
   if (!p) return BFL_OK;
   if (p->parent) cudaSetDevice(p->parent->device);
+  for (auto& kv : p->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (auto& sl : p->slots) {
     if (sl.ctx) cudaStreamSynchronize(sl.ctx->stream);
     if (sl.done) cudaEventDestroy(sl.done);
@@ -882,20 +907,14 @@ int bfl_pipe_create(bfl_ctx* c, bfl_plan* plan, int noisepoly, const bfl_noise_s
   return BFL_OK;
 }
 
-int bfl_pipe_submit(bfl_pipe* p, const double* clc, const double* sk, double* out_lnO, double thresh,
-                    bfl_region* out_regions, int64_t* out_counts, double* out_sk, int64_t* job) {
-  if (!p || !clc) return fail(BFL_ERR_ARG, "null argument to bfl_pipe_submit");
-  if (!sk && !p->have_noise) return fail(BFL_ERR_ARG, "either the noise sigmas or a noise specification is required");
-  const bool want_regions = !std::isnan(thresh);
-  if (want_regions && !out_counts) return fail(BFL_ERR_ARG, "out_counts is required when a threshold is given");
-  if (!want_regions && !out_lnO) return fail(BFL_ERR_ARG, "nothing to return: give out_lnO and/or a threshold");
-  CK(cudaSetDevice(p->parent->device));
-  bfl_pipe::Slot& sl = p->slots[(size_t)(p->submitted % (int64_t)p->slots.size())];
-  if (sl.job >= 0) CK(cudaEventSynchronize(sl.done));   // the slot's previous job must have left the device
+// everything one job enqueues on its slot's stream (also what a captured graph holds)
+static int pipe_enqueue(bfl_pipe* p, bfl_pipe::Slot& sl, const double* clc, const double* sk, double* out_lnO, double thresh,
+                        bfl_region* out_regions, int64_t* out_counts, double* out_sk) {
   bfl_ctx* c = sl.ctx;
   cudaStream_t s = c->stream;
   const int32_t B = p->B;
   const int64_t N = p->N, nk = p->k1 - p->k0;
+  const bool want_regions = !std::isnan(thresh);
   int rc;
   CK(cudaMemcpyAsync(sl.d_clc, clc, sizeof(double) * (size_t)B * N, cudaMemcpyHostToDevice, s));
   if (sk) CK(cudaMemcpyAsync(sl.d_sk, sk, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, s));
@@ -911,6 +930,63 @@ int bfl_pipe_submit(bfl_pipe* p, const double* clc, const double* sk, double* ou
       CK(cudaMemcpyAsync(out_regions, sl.d_rec, sizeof(RegionRec) * (size_t)p->max_regions, cudaMemcpyDeviceToHost, s));
   }
   if (out_lnO) CK(cudaMemcpyAsync(out_lnO, sl.d_lnO, sizeof(double) * (size_t)B * (size_t)nk, cudaMemcpyDeviceToHost, s));
+  return BFL_OK;
+}
+
+static bool host_pinned(const void* ptr) {
+  if (!ptr) return true;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int bfl_pipe_submit(bfl_pipe* p, const double* clc, const double* sk, double* out_lnO, double thresh,
+                    bfl_region* out_regions, int64_t* out_counts, double* out_sk, int64_t* job) {
+  if (!p || !clc) return fail(BFL_ERR_ARG, "null argument to bfl_pipe_submit");
+  if (!sk && !p->have_noise) return fail(BFL_ERR_ARG, "either the noise sigmas or a noise specification is required");
+  const bool want_regions = !std::isnan(thresh);
+  if (want_regions && !out_counts) return fail(BFL_ERR_ARG, "out_counts is required when a threshold is given");
+  if (!want_regions && !out_lnO) return fail(BFL_ERR_ARG, "nothing to return: give out_lnO and/or a threshold");
+  CK(cudaSetDevice(p->parent->device));
+  const int slot = (int)(p->submitted % (int64_t)p->slots.size());
+  bfl_pipe::Slot& sl = p->slots[(size_t)slot];
+  if (sl.job >= 0) CK(cudaEventSynchronize(sl.done));   // the slot's previous job must have left the device
+  cudaStream_t s = sl.ctx->stream;
+  int rc = BFL_OK;
+  bool done = false;
+  if (p->use_graphs && sl.job >= 0 && !sl.ctx->timing) {   // warm slot: scratch is sized, plans exist
+    uint64_t tb;
+    std::memcpy(&tb, &thresh, sizeof(tb));
+    bfl_pipe::GraphKey key{slot, clc, sk, out_lnO, out_regions, out_counts, out_sk, tb};
+    bfl_pipe::GraphVal& gv = p->graphs[key];
+    if (gv.exec) {
+      CK(cudaGraphLaunch(gv.exec, s));
+      sl.ctx->stats.launches += gv.launches;
+      done = true;
+    } else if (++gv.seen >= 2 && p->graphs.size() <= 64 && host_pinned(clc) && host_pinned(sk) && host_pinned(out_lnO) &&
+               host_pinned(out_regions) && host_pinned(out_counts) && host_pinned(out_sk)) {
+      const int64_t l0 = sl.ctx->stats.launches;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = pipe_enqueue(p, sl, clc, sk, out_lnO, thresh, out_regions, out_counts, out_sk);
+        const cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc == BFL_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&gv.exec, graph, 0) == cudaSuccess) {
+          gv.launches = sl.ctx->stats.launches - l0;
+          CK(cudaGraphLaunch(gv.exec, s));
+          done = true;
+        } else {
+          gv.exec = nullptr;
+          gv.seen = -1000000;          // this key cannot be captured: enqueue directly from now on
+          cudaGetLastError();
+          rc = BFL_OK;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
+  if (!done && (rc = pipe_enqueue(p, sl, clc, sk, out_lnO, thresh, out_regions, out_counts, out_sk))) return rc;
   CK(cudaEventRecord(sl.done, s));
   sl.job = p->submitted;
   sl.host_cnt = want_regions ? out_counts : nullptr;
@@ -932,6 +1008,12 @@ int bfl_pipe_wait(bfl_pipe* p, int64_t job, int32_t* nregions) {
     *nregions = (int32_t)n;
   }
   return BFL_OK;
+}
+
+int32_t bfl_pipe_graph_count(const bfl_pipe* p) {
+  int32_t n = 0;
+  if (p) for (auto& kv : p->graphs) n += kv.second.exec ? 1 : 0;
+  return n;
 }
 
 int64_t bfl_pipe_launch_count(const bfl_pipe* p) {

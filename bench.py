@@ -607,7 +607,7 @@ def run_ours(args, rank, local_rank, world):
             # oddsratio, then thresholder): the above-threshold regions with their maxima, and per-curve counts.
             "e2e": {"value": e2e_search_value, "unit": UNIT, "h2d_bytes_per_step": world * B * N * 8,
                     "d2h_bytes_per_step": world * ((B + 3) * 8 + MAXREG * 24), "steps": args.steps,
-                    "gpu_launches": int(e2e_launches),
+                    "gpu_launches": int(e2e_launches), "cuda_graphs": int(pipe.graphs),
                     "what": "bfl_pipe_submit / bfl_pipe_wait (C ABI) with page-locked host buffers, 6 jobs in flight: H2D of the "
                             "step's light curves (float64), noise sigma of every curve estimated on device (SG detrend + "
                             "periodogram), all hypotheses, region extraction, D2H of the step's region records (start, stop, "

@@ -195,6 +195,9 @@ int bfl_pipe_submit(bfl_pipe* pipe, const double* clc, const double* sk, double*
                     bfl_region* out_regions, int64_t* out_counts, double* out_sk, int64_t* job);
 int bfl_pipe_wait(bfl_pipe* pipe, int64_t job, int32_t* nregions);
 int64_t bfl_pipe_launch_count(const bfl_pipe* pipe);
+/* Jobs that reuse (slot, host buffers, threshold) are replayed as ONE CUDA graph from their second appearance on
+ * (page-locked buffers only): number of graphs instantiated so far. */
+int32_t bfl_pipe_graph_count(const bfl_pipe* pipe);
 int bfl_pipe_destroy(bfl_pipe* pipe);
 
 /* ---- injection sweep on device (scripts/flare_detection_efficiency.py:399-651; BASELINE config 5) ----

@@ -43,4 +43,4 @@ for full in (False, True):
     dt = time.perf_counter() - t0
     t1 = time.perf_counter()
     # host-side cost of submit alone (no waiting): enqueue `depth` jobs into an idle pipe
-    print("pipe B=%d depth=%d %s: %.4f ms/step, %.3e units/s" % (B, depth, "full lnO" if full else "search", 1e3 * dt / steps, B * NK * 93 * steps / dt), flush=True)
+    print("pipe B=%d depth=%d %s: %.4f ms/step, %.3e units/s, graphs %d, launches %d" % (B, depth, "full lnO" if full else "search", 1e3 * dt / steps, B * NK * 93 * steps / dt, pipe.graphs, pipe.launches), flush=True)
