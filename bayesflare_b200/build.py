@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libbfl.so")
-SOURCES = ["bfl_kernels.cu", "bfl_abi.cu"]
-DEPS = SOURCES + ["bfl_kernels.cuh", "phi_table.inc", "exphi_table.inc", "exphi2_table.inc", os.path.join(ROOT, "include", "bfl.h")]
+SOURCES = ["bfl_kernels.cu", "bfl_wsplit.cu", "bfl_abi.cu"]
+DEPS = SOURCES + ["bfl_kernels.cuh", "bfl_devmath.cuh", "phi_table.inc", "exphi_table.inc", "exphi2_table.inc", os.path.join(ROOT, "include", "bfl.h")]
 
 
 def nvcc_path() -> str:

@@ -439,6 +439,73 @@ int bfl_plan_create(bfl_ctx* c, int W, int P, const double* bgmodels, const doub
     for (int r = 0; r < S && wsep_ok; r++)
       for (int g = sg0[r]; g < sg1[r]; g++)
         if (idxB[g] != r) wsep_ok = false;
+    // split weighted form (bfl_wsplit.cu): every window sum of the weighted path is a correlation of one of the two
+    // streams 1/v, d/v with a FIXED vector -- q_p q_q and m_s^2, m_s q_p on 1/v; q_p and m_s on d/v.  Vectors are
+    // packed by support class (whole window / rise half / decay half) so the kernel's tap loops are compile-time.
+    if (wsep_ok && wsplit_window_supported(W)) {
+      const int H = W / 2, T0H = H & ~1, NTL = H + 1, NTLP = (NTL + 1) & ~1, NTHP = (W - T0H + 1) & ~1;
+      std::vector<int> shrow(S, -1), cls(S, 0);
+      int rows = P * (P + 1) / 2 + P;
+      std::vector<char> used(S, 0);                   // the centre row of a separable hypothesis is folded into its A rows
+      for (int h = 0; h < nhyp; h++) {
+        for (int i = 0; i < pv.hyp_nA[h]; i++) used[pv.hyp_A0[h] + i] = 1;
+        for (int i = 0; i < pv.hyp_nB[h]; i++) used[pv.hyp_B0[h] + i] = 1;
+      }
+      for (int r = 0; r < S; r++) {
+        if (hi[r] <= lo[r] || !used[r]) continue;     // empty shape: no rows, its sums are zero
+        shrow[r] = rows; rows += P + 2;
+        cls[r] = (hi[r] <= NTL) ? 1 : (lo[r] >= T0H ? 2 : 0);
+      }
+      std::vector<double> tab;
+      std::vector<int> joff, jrow;
+      int njc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      auto push = [&](int cl, int row, auto&& val) {     // val(w): the vector's value at tap w
+        const int t0 = cl == 2 ? T0H : 0, nt = cl == 0 ? W : (cl == 1 ? NTL : W - T0H), np = cl == 0 ? WP : (cl == 1 ? NTLP : NTHP);
+        joff.push_back((int)tab.size()); jrow.push_back(row);
+        for (int w = 0; w < np; w++) tab.push_back(w < nt ? val(t0 + w) : 0.0);
+      };
+      for (int st = 0; st < 2; st++)
+        for (int cl = 0; cl < 3; cl++) {
+          const size_t before = joff.size();
+          if (cl == 0) {
+            if (st == 0) {
+              int row = 0;
+              for (int a = 0; a < P; a++)
+                for (int b = a; b < P; b++, row++)
+                  push(0, row, [&](int w) { return qb[(size_t)a * WP + w] * qb[(size_t)b * WP + w]; });
+            } else {
+              for (int a = 0; a < P; a++) push(0, P * (P + 1) / 2 + a, [&](int w) { return qb[(size_t)a * WP + w]; });
+            }
+          }
+          for (int r = 0; r < S; r++) {
+            if (shrow[r] < 0 || cls[r] != cl) continue;
+            const double* m = hs.data() + (size_t)r * WP;
+            if (st == 0) {
+              for (int a = 0; a < P; a++) push(cl, shrow[r] + a, [&](int w) { return m[w] * qb[(size_t)a * WP + w]; });
+              push(cl, shrow[r] + P, [&](int w) { return m[w] * m[w]; });
+            } else {
+              push(cl, shrow[r] + P + 1, [&](int w) { return m[w]; });
+            }
+          }
+          njc[st][cl] = (int)(joff.size() - before);
+        }
+      void *d_wtab, *d_woff, *d_wrow, *d_wshrow;
+      if ((rc = plan_alloc(p, sizeof(double) * tab.size(), &d_wtab)) || (rc = plan_alloc(p, sizeof(int) * joff.size(), &d_woff)) ||
+          (rc = plan_alloc(p, sizeof(int) * jrow.size(), &d_wrow)) || (rc = plan_alloc(p, sizeof(int) * (size_t)S, &d_wshrow))) {
+        bfl_plan_destroy(p);
+        return rc;
+      }
+      CKP(cudaMemcpyAsync(d_wtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, s));
+      CKP(cudaMemcpyAsync(d_woff, joff.data(), sizeof(int) * joff.size(), cudaMemcpyHostToDevice, s));
+      CKP(cudaMemcpyAsync(d_wrow, jrow.data(), sizeof(int) * jrow.size(), cudaMemcpyHostToDevice, s));
+      CKP(cudaMemcpyAsync(d_wshrow, shrow.data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, s));
+      CKP(cudaStreamSynchronize(s));
+      pv.wc_tab = (const double*)d_wtab; pv.wc_off = (const int*)d_woff; pv.wc_row = (const int*)d_wrow;
+      pv.wc_shrow = (const int*)d_wshrow;
+      pv.wc_tab_len = (int)tab.size(); pv.wc_nj = (int)joff.size(); pv.wc_rows = rows;
+      for (int st = 0; st < 2; st++)
+        for (int cl = 0; cl < 3; cl++) pv.wc_n[st][cl] = njc[st][cl];
+    }
     CKP(cudaMemcpyAsync(d_shg0, sg0.data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, s));
     CKP(cudaMemcpyAsync(d_shg1, sg1.data(), sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, s));
     CKP(cudaMemcpyAsync(d_shlo, lo.data(), sizeof(short) * (size_t)S, cudaMemcpyHostToDevice, s));
@@ -531,6 +598,13 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
   if (need_general) {
     if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
     if ((rc = c->get("uu", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.uu = (double*)ptr;
+  }
+  sc.Yw = nullptr; sc.Yw_curves = 0;
+  if (one_chunk && !sv.const_var && wsplit_fits(pv)) {   // weighted path, split form: window sums of a chunk of curves
+    int ch = 1;
+    const size_t bytes = wsplit_scratch_bytes(pv, sv.B, nk, &ch);
+    if ((rc = c->get("Yw", bytes, &ptr))) return rc;
+    sc.Yw = (double*)ptr; sc.Yw_curves = ch;
   }
   sc.part = nullptr;
   if (need_part) {

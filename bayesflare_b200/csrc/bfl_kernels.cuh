@@ -54,6 +54,14 @@ struct PlanView {
   const int* sh_g1;
   int hyp_B0[MAXH];          // global shape index of the hypothesis' first B shape
   int hyp_nB[MAXH];          // number of B shapes
+  // ---- split weighted form (bfl_wsplit.cu): the fixed vectors the streams 1/v and d/v are correlated with, packed by
+  // (stream, support class) in that order; nullptr when the plan has no such form
+  const double* wc_tab;      // packed vectors: whole-window rows of WP doubles, rise-half rows, decay-half rows
+  const int* wc_off;         // [wc_nj] offset of a vector in wc_tab (doubles)
+  const int* wc_row;         // [wc_nj] row of the sums array Yw it produces
+  const int* wc_shrow;       // [S] first Yw row of shape s (f_0..f_{P-1}, e, r0), -1 for an empty shape
+  int wc_n[2][3];            // vectors per (stream: 1/v, d/v) x (class: whole window, rise half, decay half)
+  int wc_tab_len, wc_nj, wc_rows;   // rows: P(P+1)/2 of Q U Q^T, P of Q U d, P + 2 per non-empty shape
   // ---- per-plan shared-memory block of k_epilogue2 (tables, per-template weights, run lists), built once at
   // plan creation for noisepoly = 0 / 1; nullptr when the plan does not fit that kernel
   const void* epi2_block[2];
@@ -82,6 +90,8 @@ struct Scratch {
   unsigned long long* tile_counters;  // [NC] dynamic tile scheduler state
   unsigned long long* split_counters; // [4] split form: self-resetting tile schedulers + exit counters
   double* Y;       // [S][B*nk] shape correlations (split form) or nullptr
+  double* Yw;      // [wc_rows][Bc*nk] window sums of the split weighted form for a chunk of Bc curves, or nullptr
+  int Yw_curves;   // Bc
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
@@ -92,6 +102,31 @@ struct LaunchStats { int64_t launches = 0; };
 
 // one above-threshold region of one light curve (same layout as bfl_region in include/bfl.h)
 struct RegionRec { int32_t curve, start, stop, argmax; double maxval; };
+
+// arguments of the separable weighted kernels (k_window_wsep in bfl_kernels.cu, k_window_wsep2 in bfl_wsep2.cu)
+struct WsepArgs {
+  const double* dw; const double* uu;
+  int64_t seglen, N, seg0, k0, k1;
+  int B, tiles_per_curve;
+  int64_t total_tiles;
+  const double* rshapes; const short* sh_lo; const short* sh_hi; const int* sh_g0; const int* sh_g1;
+  const double* qb; const double* lp; const double* lw; const short* idxA;
+  int G, W, WP, S, nhyp, arows;
+  int hyp_begin[MAXH + 1];
+  int hyp_half[MAXH];
+  int hyp_A0[MAXH], hyp_nA[MAXH], hyp_B0[MAXH], hyp_nB[MAXH];
+  double logdetG;
+  double2* part;
+  double* bgabs;
+};
+
+// split weighted form (bfl_wsplit.cu): k_wcorr (window sums of both streams -> Yw) + k_wsolve (per-sample Cholesky,
+// per-shape solves, per-template terms, log-sum-exp); Yw makes one round trip through HBM per chunk of curves
+bool wsplit_window_supported(int W);
+bool wsplit_fits(const PlanView& pv);
+size_t wsplit_scratch_bytes(const PlanView& pv, int B, int64_t nk, int* chunk_curves);
+cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* Yw, int chunk_curves, int sms,
+                                 cudaStream_t s, LaunchStats* st);
 
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
                                  double* d_raw, cudaStream_t s, LaunchStats* st);
