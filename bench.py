@@ -642,8 +642,42 @@ def run_ours(args, rank, local_rank, world):
     if weak is not None:
         line["weak_scaling"] = weak
 
+    if world == 1:
+        # ---- the WEIGHTED path (row f4: every real Kepler file carries per-sample errors, so v_j = sk^2 + cle_j^2 varies
+        # along the window): the same curves with synthetic flux errors through k_wcorr + k_wsolve, device-resident
+        Bw = min(256, B)
+        rngw = np.random.default_rng(6)
+        cle_w = 0.3 + 0.2 * rngw.random((Bw, N)) + 0.05 * np.sin(np.arange(N) / 50.)[None, :]
+        d_clew = torch.from_numpy(cle_w).to(dev)
+        d_outw = torch.empty((Bw, NK), dtype=torch.float64, device=dev)
+
+        def weighted_step():
+            plan.detector_odds_dev(d_in[0].data_ptr(), d_clew.data_ptr(), False, d_sk[0].data_ptr(), Bw, N, 0, N, K0, K1,
+                                   d_outw.data_ptr(), ctx=ctxs[0])
+        with torch.cuda.stream(streams[0]):
+            for _ in range(2):
+                weighted_step()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = 5
+            ev0.record(streams[0])
+            for _ in range(nrep):
+                weighted_step()
+            ev1.record(streams[0])
+        torch.cuda.synchronize()
+        ms_w = ev0.elapsed_time(ev1) / nrep
+        lnO_w = d_outw[0].cpu().numpy()
+        line["weighted_path"] = {"value": Bw * NK * G_EVAL / (ms_w * 1e-3), "unit": UNIT, "curves": Bw, "samples": N, "ms_per_call": ms_w,
+                                 "what": "bfl_detector_odds_dev with per-sample flux errors (k_prep_whiten, k_wcorr, k_wsolve, k_combine), "
+                                         "inputs resident, CUDA events around %d calls" % nrep}
+
     if not args.no_cpu_baseline and world == 1:
         cores = set_host_threads()
+        from oracle import oracle as orc_w
+        ref_w, _ = orc_w.oddsratio(clc0[0], cle_w[0], cts, sk=float(sk[0]))
+        ref_w = np.asarray(ref_w)
+        if ref_w.shape[0] == N:
+            ref_w = ref_w[K0:K1]                 # (the oracle drops the truncated-window samples itself by default)
+        line["weighted_path"]["parity_vs_oracle_curve0"] = float(np.max(np.abs(lnO_w - ref_w) / np.maximum(1.0, np.abs(ref_w))))
         nc = min(args.cpu_curves, B)
         ups, secs, ref0, done = cpu_oracle_throughput(cts, clc0[:nc], max_seconds=12.0)
         got0 = plan.detector_odds(clc0[0], None, sk[0], k0=K0, k1=K1)
