@@ -386,10 +386,14 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
   };
   auto take = [&](int n, double (&F)[NV]) {
     cp_async_wait_pending<KD - 1>();
-    const bool have = sSeq[n] >= 0;
     const unsigned src = ring + (unsigned)(n & (KD - 1)) * RS;
+    if (sSeq[n] >= 0) {                            // (warp-uniform)
 #pragma unroll
-    for (int q = 0; q < NV; q++) F[q] = have ? lds_f64(src + q * RQ) : 0.0;
+      for (int q = 0; q < NV; q++) F[q] = lds_f64(src + q * RQ);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NV; q++) F[q] = 0.0;
+    }
     issue(n + KD);
   };
   // (f, e, r0) -> (y = L^-1 f, s' = e - |y|^2, r' = r0 - y.yc)
@@ -406,6 +410,32 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
     for (int i = 0; i < P; i++) { s = fma(-V[i], V[i], s); r = fma(-V[i], myL[(NLI + i) * TPB], r); }
     V[P] = s;
     V[P + 1] = r;
+  };
+
+  // two shapes at once: the factor is read once and the two dependency chains interleave
+  auto solve2 = [&](const double (&F0)[NV], const double (&F1)[NV], double (&V0)[NV], double (&V1)[NV]) {
+    double s0 = F0[P], r0 = F0[P + 1], s1 = F1[P], r1 = F1[P + 1];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const double l0 = myL[(i * (i + 1) / 2) * TPB];
+      double y0 = l0 * F0[0], y1 = l0 * F1[0];
+#pragma unroll
+      for (int q = 1; q <= i; q++) {
+        const double l = myL[(i * (i + 1) / 2 + q) * TPB];
+        y0 = fma(l, F0[q], y0);
+        y1 = fma(l, F1[q], y1);
+      }
+      V0[i] = y0;
+      V1[i] = y1;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      const double c = myL[(NLI + i) * TPB];
+      s0 = fma(-V0[i], V0[i], s0); r0 = fma(-V0[i], c, r0);
+      s1 = fma(-V1[i], V1[i], s1); r1 = fma(-V1[i], c, r1);
+    }
+    V0[P] = s0; V0[P + 1] = r0;
+    V1[P] = s1; V1[P + 1] = r1;
   };
 
   // One pass over the hypotheses.  LIN: linear-domain sums, returns true when this sample has to be redone.
@@ -425,10 +455,12 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
       double S = 0.0, zz = 0.0;                     // LIN: the sum, the largest z^2 of a full-range hypothesis
       unsigned kmax = 0;                            // LIN: the largest table index (half-range)
       double mx = LSE_EMPTY, sm = 0.0;              // LOG
-      auto lin_term = [&](double s, double r, double c) {
+      // HALF is a compile-time tag: with a run-time branch inside, every term is its own basic block and the K
+      // dependency chains of a group are scheduled one after the other instead of interleaved
+      auto lin_term = [&](auto half_tag, double s, double r, double c) {
         const double w = rsqrt_seeded(s);
         const double z = r * w;
-        if (half) {
+        if constexpr (decltype(half_tag)::value) {
           S = fma(c * w, exphi2_one(z + ZC, aT, kmax), S);
         } else {
           const double q = z * z;
@@ -453,8 +485,13 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
       auto many = [&](auto ktag, const double* sv, const double* rv, const double* cw, const int* gi) {
         constexpr int K = decltype(ktag)::value;
         if constexpr (LIN) {
+          if (half) {
 #pragma unroll
-          for (int c = 0; c < K; c++) lin_term(sv[c], rv[c], cw[c]);
+            for (int c = 0; c < K; c++) lin_term(std::true_type{}, sv[c], rv[c], cw[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < K; c++) lin_term(std::false_type{}, sv[c], rv[c], cw[c]);
+          }
         } else {
           double x[K], w[K];
 #pragma unroll
@@ -467,18 +504,25 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
         // pairs with the A shapes its row of the weight table admits
         double yA[NA][P];
 #pragma unroll
-        for (int i = 0; i < NA; i++) {
-          const bool have = i < nA;
-          double F[NV], V[NV];
-          if (have) {
-            if constexpr (LIN) take(nsh++, F);
-            else load_shape(A0 + i, F);
-            solve(F, V);
+        for (int i = 0; i < NA; i += 2) {
+          double F0[NV], F1[NV], V0[NV], V1[NV];
+#pragma unroll
+          for (int q = 0; q < NV; q++) { V0[q] = 0.0; V1[q] = 0.0; }
+          if (i + 1 < nA) {
+            if constexpr (LIN) { take(nsh++, F0); take(nsh++, F1); }
+            else { load_shape(A0 + i, F0); load_shape(A0 + i + 1, F1); }
+            solve2(F0, F1, V0, V1);
+          } else if (i < nA) {
+            if constexpr (LIN) take(nsh++, F0);
+            else load_shape(A0 + i, F0);
+            solve(F0, V0);
           }
 #pragma unroll
-          for (int q = 0; q < P; q++) yA[i][q] = have ? V[q] : 0.0;
-          myAB[(2 * i) * TPB] = have ? V[P] : 0.0;
-          myAB[(2 * i + 1) * TPB] = have ? V[P + 1] : 0.0;
+          for (int q = 0; q < P; q++) { yA[i][q] = V0[q]; yA[i + 1][q] = V1[q]; }
+          myAB[(2 * i) * TPB] = V0[P];
+          myAB[(2 * i + 1) * TPB] = V0[P + 1];
+          myAB[(2 * i + 2) * TPB] = V1[P];
+          myAB[(2 * i + 3) * TPB] = V1[P + 1];
         }
         for (int j = 0; j < nB; j++) {
           double F[NV], V[NV];
@@ -487,7 +531,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
           solve(F, V);
           const double* cw = sC + (size_t)(B0 + j) * NA;
           const int* gi = sGi + (size_t)(B0 + j) * NA;
-          // A shapes four at a time, the remainder (NA mod 4) two at a time
+          // A shapes five at a time: five independent dependency chains per basic block
           auto group = [&](auto itag, auto ktag) {
             constexpr int I0 = decltype(itag)::value, K = decltype(ktag)::value;
             bool any = false;
@@ -506,9 +550,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
             many(ktag, sv, rv, cw + I0, gi + I0);
           };
           static_assert(NA == 10, "the grouping below is written for ten A shapes");
-          group(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
-          group(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
-          group(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+          group(std::integral_constant<int, 0>{}, std::integral_constant<int, 5>{});
+          group(std::integral_constant<int, 5>{}, std::integral_constant<int, 5>{});
         }
       } else {
         // dense hypothesis: one template per shape, two shapes at a time
@@ -527,8 +570,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
             load_shape(B0 + j, F0);
             load_shape(B0 + j1, F1);
           }
-          solve(F0, V0);
-          solve(F1, V1);
+          solve2(F0, F1, V0, V1);
           const double cw[2] = {sC[(size_t)(B0 + j) * NA], (j + 1 < nB) ? sC[(size_t)(B0 + j1) * NA] : 0.0};
           const int gi[2] = {sGi[(size_t)(B0 + j) * NA], (j + 1 < nB) ? sGi[(size_t)(B0 + j1) * NA] : -1};
           const double sv[2] = {V0[P], V1[P]}, rv[2] = {V0[P + 1], V1[P + 1]};
