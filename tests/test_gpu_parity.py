@@ -514,6 +514,44 @@ def test_weighted_batch_rows_equal_single_curves_and_full_lnB():
     assert_logodds_close(Bf.bayes_factors_marg_poly_bgd_only(), refbg, TOL, "weighted bg only")
 
 
+_SPLIT_VS_ONE_KERNEL = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+import bayesflare_b200 as bf
+rng = np.random.default_rng(31)
+B, N, DT = 5, 700, 1765.55929
+ts = np.arange(N) * DT
+clc = rng.standard_normal((B, N)) + 2.0 * np.sin(2 * np.pi * ts / (2.7 * 86400.))[None, :]
+clc[2, 300:306] += np.array([9., 7., 5., 3.5, 2., 1.])
+clc[4, 500] = np.nan
+cle = 0.3 + 0.25 * rng.random((B, N))
+det = bf.OddsRatioDetector(bf.Lightcurve(cts=ts, clc=clc[0], cle=cle[0]))
+np.save(sys.argv[1], det.oddsratio_batch(clc, sk=np.full(B, 0.9), cle=cle))
+"""
+
+
+@pytest.mark.gpu
+def test_weighted_split_form_in_chunks_equals_the_one_kernel_form(tmp_path):
+    """k_wcorr + k_wsolve with a 1 MB cap on the window-sum scratch (one curve per chunk, five chunks; a flare, so
+    the log-domain fallback runs; a NaN) against k_window_wsep -- two processes, the switches are read once"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "run.py"
+    script.write_text(_SPLIT_VS_ONE_KERNEL % {"root": root})
+    outs = []
+    for name, env in (("split", {"BFL_WSPLIT_CAP_MB": "1"}), ("one", {"BFL_NO_WSPLIT": "1"})):
+        out = tmp_path / (name + ".npy")
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=dict(os.environ, **env), timeout=300)
+        outs.append(np.load(out))
+    split, one = outs
+    np.testing.assert_array_equal(np.isfinite(split), np.isfinite(one))
+    assert np.count_nonzero(~np.isfinite(split[4])) == 55 and np.all(np.isfinite(split[:4]))
+    ok = np.isfinite(one)
+    assert np.max(np.abs(split[ok] - one[ok]) / np.maximum(1.0, np.abs(one[ok]))) <= 1e-10
+    assert one[2].max() > 16.5 and int(np.argmax(split[2])) == int(np.argmax(one[2]))
+
+
 @pytest.mark.gpu
 def test_weighted_path_non_finite_samples():
     """a NaN in the data poisons exactly the windows that contain it (log_marg_amp_full.c:20,25)"""
