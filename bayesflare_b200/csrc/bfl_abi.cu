@@ -599,7 +599,7 @@ static int setup_scratch(bfl_ctx* c, const PlanView& pv, const SeriesView& sv, b
     if ((rc = c->get("dw", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.dw = (double*)ptr;
     if ((rc = c->get("uu", sizeof(double) * (size_t)sv.B * sv.seglen, &ptr))) return rc; sc.uu = (double*)ptr;
   }
-  sc.Yw = nullptr; sc.Yw_curves = 0;
+  sc.Yw = nullptr; sc.Yw_curves = 0; sc.Yw_lnO = nullptr; sc.Yw_noisepoly = 0;
   if (one_chunk && !sv.const_var && wsplit_fits(pv)) {   // weighted path, split form: window sums of a chunk of curves
     int ch = 1;
     const size_t bytes = wsplit_scratch_bytes(pv, sv.B, nk, &ch);
@@ -673,9 +673,13 @@ static int detector_run(bfl_ctx* c, bfl_plan* p, int noisepoly, const SeriesView
   } else if (wsep || weighted_fits(pv, sc)) {
     std::pair<cudaEvent_t, cudaEvent_t> pr;
     if (c->timing && (rc = timing_begin(c, pr))) return rc;
+    // split weighted form without truncated windows or marginal outputs: k_wsolve folds the hypotheses itself
+    const bool fold = wsep && sc.Yw && !edges && !d_marg;
+    if (fold) { sc.Yw_lnO = d_lnO; sc.Yw_noisepoly = noisepoly; }
     if (wsep) CK(launch_window_wsep_lse(pv, sv, sc, s, &c->stats));
     else CK(launch_window_weighted_lse(pv, sv, sc, s, &c->stats));
     if (c->timing) { CK(cudaEventRecord(pr.second, s)); c->tev.push_back(pr); }
+    if (fold) return BFL_OK;
     if (edges) CK(launch_window_general_lse(pv, sv, sc, true, s, &c->stats));
   } else {
     CK(launch_window_general_lse(pv, sv, sc, false, s, &c->stats));

@@ -92,6 +92,8 @@ struct Scratch {
   double* Y;       // [S][B*nk] shape correlations (split form) or nullptr
   double* Yw;      // [wc_rows][Bc*nk] window sums of the split weighted form for a chunk of Bc curves, or nullptr
   int Yw_curves;   // Bc
+  double* Yw_lnO;  // split weighted form: combine the hypotheses in k_wsolve and write the log odds here (or nullptr)
+  int Yw_noisepoly;
   int NC;          // number of template chunks
   int gchunk;      // templates per chunk
   int KT;          // samples per thread of the fast kernel
@@ -125,8 +127,9 @@ struct WsepArgs {
 bool wsplit_window_supported(int W);
 bool wsplit_fits(const PlanView& pv);
 size_t wsplit_scratch_bytes(const PlanView& pv, int B, int64_t nk, int* chunk_curves);
+// d_lnO not null: k_wsolve also combines the hypotheses (no partial sums, no k_combine) and writes the log odds
 cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* Yw, int chunk_curves, int sms,
-                                 cudaStream_t s, LaunchStats* st);
+                                 double* d_lnO, int noisepoly, cudaStream_t s, LaunchStats* st);
 
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
                                  double* d_raw, cudaStream_t s, LaunchStats* st);

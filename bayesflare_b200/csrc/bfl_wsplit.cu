@@ -170,6 +170,8 @@ struct WSolveArgs {
   double logdetG;
   double2* part;
   double* bgabs;
+  double* lnO;                             // not null: combine the hypotheses here (find.py:853-862) and write the log odds
+  int noisepoly;
 };
 
 constexpr int WS_TPB = 128, WS_MINB = 2;   // one sample per thread, two CTAs (8 warps) per SM: 255 registers, no spills
@@ -230,7 +232,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
   double* sRef = sK + ((a.G + 1) & ~1);            // [MAXH] reference value of a hypothesis' linear sum
   double* sL = sRef + MAXH;                        // [NL][TPB] per-thread L^-1 (packed) and yc
   double* sAB = sL + (size_t)NL * TPB;             // [2 NA][TPB] per-thread s'_A, r'_A
-  double* sRing = sAB + (size_t)2 * NA * TPB;      // [TPB / 32][KD][NV][32] prefetched window sums
+  double* sRel = sAB + (size_t)2 * NA * TPB;       // [MAXH][TPB] per-thread log marginal of every hypothesis (fused combine)
+  double* sRing = sRel + (size_t)MAXH * TPB;       // [TPB / 32][KD][NV][32] prefetched window sums
   int* sShRow = reinterpret_cast<int*>(sRing + (size_t)(TPB / 32) * KD * NV * 32);   // [S]
   int* sGi = sShRow + a.S;                         // [S][NA] template index of (s, i) or -1
   int* sSeq = sGi + (size_t)a.S * NA;              // [S + 1] Yw rows of the shapes in the order a sample consumes them (-1: empty
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
   const unsigned aT = (unsigned)__cvta_generic_to_shared(sT);
   double* myL = sL + tid;
   double* myAB = sAB + tid;
+  double* myRel = sRel + tid;
   const int64_t BK = a.BK;
   const int nseq = sSeq[a.S];
   const unsigned ring = (unsigned)__cvta_generic_to_shared(sRing + (size_t)(tid >> 5) * KD * NV * 32 + lane);
@@ -581,15 +585,34 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
         big = big || (!bad && (kmax > (unsigned)(BFL_EXPHI2_NI - 1) || zz > ZC * ZC || !(S > 0.0 && S < 1.0e300)));
         double m = sRef[h] + hc + (half ? 0.0 : 0.5 * ZC * ZC);
         if (bad) { m = lnBbg - lnBbg; S = m; }       // NaN, as (-inf) - (-inf) in the general path
-        if (active) a.part[(size_t)h * a.part_stride + ko] = make_double2(m, S);
+        if (a.lnO) myRel[h * TPB] = (m != m || S != S) ? m + S : ((S > 0.0) ? m + log(S) : neg_inf());   // as k_combine
+        else if (active) a.part[(size_t)h * a.part_stride + ko] = make_double2(m, S);
       } else {
         if (bad) { mx = lnBbg - lnBbg; sm = mx; }
-        if (active) a.part[(size_t)h * a.part_stride + ko] = make_double2(mx + hc, sm);
+        if (a.lnO) myRel[h * TPB] = (mx != mx || sm != sm) ? mx + sm : ((sm > 0.0) ? (mx + hc) + log(sm) : neg_inf());
+        else if (active) a.part[(size_t)h * a.part_stride + ko] = make_double2(mx + hc, sm);
       }
     }
     return big;
   };
   if (hypotheses(std::true_type{})) hypotheses(std::false_type{});
+  if (a.lnO && active) {
+    // the reference's fold (find.py:853-862; the same arithmetic as k_combine): numerator = the signal hypothesis,
+    // denominator = logplus over [polynomial-only (= 0 in these units), noise models]
+    const bool h0 = a.hyp_begin[0] < a.hyp_begin[1];
+    double lnO = h0 ? myRel[0] : neg_inf();
+    const int nnoise = a.nhyp - 1 + (a.noisepoly ? 1 : 0);
+    if (nnoise > 0) {
+      double denom = neg_inf();
+      if (a.noisepoly) denom = logplus_dev(denom, 0.0);
+      for (int h = 1; h < a.nhyp; h++)
+        denom = logplus_dev(denom, (a.hyp_begin[h] < a.hyp_begin[h + 1]) ? myRel[h * TPB] : neg_inf());
+      lnO = lnO - denom;
+    } else {
+      lnO = lnO + lnBbg;                            // no noise models: signal versus Gaussian noise
+    }
+    a.lnO[ko] = lnO;
+  }
   }   // warp-tile loop
 }
 
@@ -606,7 +629,7 @@ static size_t wcorr_smem(const PlanView& pv) {
 static size_t wsolve_smem(const PlanView& pv) {
   const int NL = pv.P * (pv.P + 1) / 2 + pv.P;
   return sizeof(double) * ((size_t)((BFL_EXPHI2_NI + 1) & ~1) + (size_t)pv.S * WS_NA + (size_t)((pv.G + 1) & ~1) + MAXH +
-                           (size_t)(NL + 2 * WS_NA) * WS_TPB + (size_t)(WS_TPB / 32) * WS_KD * (pv.P + 2) * 32) +
+                           (size_t)(NL + 2 * WS_NA + MAXH) * WS_TPB + (size_t)(WS_TPB / 32) * WS_KD * (pv.P + 2) * 32) +
          sizeof(int) * ((size_t)pv.S * (WS_NA + 1) + (size_t)((pv.S + 2) & ~1));
 }
 
@@ -645,7 +668,7 @@ static cudaError_t launch_wsolve(const WSolveArgs& ws, size_t smem, int sms, cud
 }
 
 cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* Yw, int chunk_curves, int sms,
-                                 cudaStream_t s, LaunchStats* st) {
+                                 double* d_lnO, int noisepoly, cudaStream_t s, LaunchStats* st) {
   const int64_t nk = a.k1 - a.k0;
   const size_t smem_c = wcorr_smem(pv), smem_s = wsolve_smem(pv);
   cudaError_t e = cudaFuncSetAttribute(k_wcorr<WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
@@ -687,6 +710,7 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
       ws.hyp_A0[h] = a.hyp_A0[h]; ws.hyp_nA[h] = a.hyp_nA[h]; ws.hyp_B0[h] = a.hyp_B0[h]; ws.hyp_nB[h] = a.hyp_nB[h];
     }
     ws.logdetG = a.logdetG; ws.part = a.part; ws.bgabs = a.bgabs;
+    ws.lnO = d_lnO; ws.noisepoly = noisepoly;
     switch (pv.P) {
       case 1: e = launch_wsolve<1>(ws, smem_s, sms, s); break;
       case 2: e = launch_wsolve<2>(ws, smem_s, sms, s); break;
