@@ -667,7 +667,7 @@ def run_ours(args, rank, local_rank, world):
         ms_w = ev0.elapsed_time(ev1) / nrep
         lnO_w = d_outw[0].cpu().numpy()
         line["weighted_path"] = {"value": Bw * NK * G_EVAL / (ms_w * 1e-3), "unit": UNIT, "curves": Bw, "samples": N, "ms_per_call": ms_w,
-                                 "what": "bfl_detector_odds_dev with per-sample flux errors (k_prep_whiten, k_wcorr, k_wsolve, k_combine), "
+                                 "what": "bfl_detector_odds_dev with per-sample flux errors (k_prep_whiten, k_wcorr, k_wsolve with the hypotheses folded in), "
                                          "inputs resident, CUDA events around %d calls" % nrep}
 
     if not args.no_cpu_baseline and world == 1:
