@@ -2609,7 +2609,7 @@ cudaError_t launch_window_wsep_lse(const PlanView& pv, const SeriesView& sv, Scr
   const int sms = sm_count_current();
   cudaError_t e = cudaSuccess;
   // large plans of the default window length: split form (bfl_wsplit.cu), Yw sized by setup_scratch
-  if (sc.Yw) return launch_window_wsplit(pv, a, sc.Yw, sc.Yw_curves, sms, sc.Yw_lnO, sc.Yw_noisepoly, s, st);
+  if (sc.Yw) return launch_window_wsplit(pv, a, sc.Yw, sc.Yw_curves, sms, sc.Yw_lnO, sc.Yw_noisepoly, sc.split_counters, s, st);
   dim3 grid((unsigned)std::min<int64_t>(a.total_tiles, sms));   // persistent: one CTA per SM (shared-memory bound)
 #define BFL_WS(P_)                                                                                              \
   case P_:                                                                                                      \

@@ -129,7 +129,8 @@ bool wsplit_fits(const PlanView& pv);
 size_t wsplit_scratch_bytes(const PlanView& pv, int B, int64_t nk, int* chunk_curves);
 // d_lnO not null: k_wsolve also combines the hypotheses (no partial sums, no k_combine) and writes the log odds
 cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* Yw, int chunk_curves, int sms,
-                                 double* d_lnO, int noisepoly, cudaStream_t s, LaunchStats* st);
+                                 double* d_lnO, int noisepoly, unsigned long long* counters, cudaStream_t s,
+                                 LaunchStats* st);
 
 cudaError_t launch_gen_templates(const TemplDesc* d_desc, int G, const double* d_mts, int W, int WP,
                                  double* d_raw, cudaStream_t s, LaunchStats* st);

@@ -172,6 +172,8 @@ struct WSolveArgs {
   double* bgabs;
   double* lnO;                             // not null: combine the hypotheses here (find.py:853-862) and write the log odds
   int noisepoly;
+  unsigned long long* tile_counter;        // next warp tile: tiles with a flare cost a second pass, a static split leaves
+  unsigned long long* done_counter;        // SMs idle (ncu: 23 % of the launch); the last warp to leave re-arms both
 };
 
 constexpr int WS_TPB = 128, WS_MINB = 2;   // one sample per thread, two CTAs (8 warps) per SM: 255 registers, no spills
@@ -276,7 +278,17 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
   const unsigned ring = (unsigned)__cvta_generic_to_shared(sRing + (size_t)(tid >> 5) * KD * NV * 32 + lane);
   constexpr unsigned RQ = 32 * 8, RS = NV * RQ;    // bytes between the values of a shape, between ring slots
 
-  for (int64_t wt = (int64_t)blockIdx.x * (TPB / 32) + (tid >> 5); wt < a.total_wtiles; wt += (int64_t)gridDim.x * (TPB / 32)) {
+  for (;;) {
+  long long wt = 0;
+  if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
+  wt = __shfl_sync(FULL, wt, 0);
+  if (wt >= a.total_wtiles) {
+    if (lane == 0 && atomicAdd(a.done_counter, 1ULL) == (unsigned long long)gridDim.x * (TPB / 32) - 1ULL) {
+      *a.tile_counter = 0ULL;
+      *a.done_counter = 0ULL;
+    }
+    break;
+  }
   const int64_t kif = wt * 32 + lane;
   bool active = kif < BK;
   {
@@ -668,7 +680,8 @@ static cudaError_t launch_wsolve(const WSolveArgs& ws, size_t smem, int sms, cud
 }
 
 cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* Yw, int chunk_curves, int sms,
-                                 double* d_lnO, int noisepoly, cudaStream_t s, LaunchStats* st) {
+                                 double* d_lnO, int noisepoly, unsigned long long* counters, cudaStream_t s,
+                                 LaunchStats* st) {
   const int64_t nk = a.k1 - a.k0;
   const size_t smem_c = wcorr_smem(pv), smem_s = wsolve_smem(pv);
   cudaError_t e = cudaFuncSetAttribute(k_wcorr<WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
@@ -711,6 +724,7 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
     }
     ws.logdetG = a.logdetG; ws.part = a.part; ws.bgabs = a.bgabs;
     ws.lnO = d_lnO; ws.noisepoly = noisepoly;
+    ws.tile_counter = counters; ws.done_counter = counters + 2;
     switch (pv.P) {
       case 1: e = launch_wsolve<1>(ws, smem_s, sms, s); break;
       case 2: e = launch_wsolve<2>(ws, smem_s, sms, s); break;
