@@ -20,10 +20,13 @@ plan.ctx.sync()
 dt = (time.perf_counter() - t0) / 3
 ms, n = plan.ctx.window_time()
 units = B * (N - 54) * det.ngrid_eval
-tag = "general" if os.environ.get("BFL_NO_WEIGHTED") else ("weighted" if os.environ.get("BFL_NO_WSEP") else "wsep")
+# which kernels ran: BFL_NO_WSPLIT=1 -> k_window_wsep (one-kernel separable form), BFL_NO_WSEP=1 -> k_window_weighted (dense),
+# BFL_NO_WEIGHTED=1 on top -> reference-order general path; default -> split form (k_wcorr + k_wsolve)
+tag = ("general" if os.environ.get("BFL_NO_WEIGHTED") and os.environ.get("BFL_NO_WSEP") else
+       "weighted" if os.environ.get("BFL_NO_WSEP") else "wsep" if os.environ.get("BFL_NO_WSPLIT") else "wsplit")
 print(tag, "B", B, "s/call %.5f" % dt, "units/s %.3e" % (units / dt), "window kernel ms/call %.3f launches/call %d -> %.3e units/s" % (ms / 3, n // 3, units / (ms / 3e3) if ms else 0))
 os.makedirs("gpurun_out", exist_ok=True); np.save("/tmp/wgt_%s_%d.npy" % (tag, B), out)
-g = "/tmp/wgt_general_%d.npy" % B
-if tag != "general" and os.path.exists(g):
+g = "/tmp/wgt_wsep_%d.npy" % B
+if tag != "wsep" and os.path.exists(g):
     g = np.load(g)
-    print("   max scaled diff vs general", np.max(np.abs(g - out) / np.maximum(1, np.abs(g))))
+    print("   max scaled diff vs the one-kernel form (wsep)", np.max(np.abs(g - out) / np.maximum(1, np.abs(g))))

@@ -1,6 +1,6 @@
-"""Per-kernel times of the split weighted form (k_wcorr, k_wsolve) on B curves x 4400 samples: torch profiler-free,
-CUDA events around repeated bfl_detector_odds_dev calls with one of the two kernels' share read from ncu instead;
-here: total window time per call and the derived units/s, for several B."""
+"""Window-stage time of the weighted path (k_wcorr + k_wsolve by default) through bfl_detector_odds with host buffers, for
+several batch sizes: CUDA events around the stage (bfl_ctx_set_timing), five calls each.
+    python tools/time_wsplit.py 256 1024"""
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd())
 import bayesflare_b200 as bf
