@@ -21,7 +21,6 @@
 // instructions for 64 DFMAs; a two-threads-per-sample variant of it was measured no faster (round 2).
 #include "bfl_kernels.cuh"
 
-#include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 #include <type_traits>
@@ -163,7 +162,7 @@ struct WSolveArgs {
   int64_t total_wtiles;                    // warp tiles of 16 samples
   const int* shrow;
   const double* lp; const double* lw; const short* idxA; const int* sh_g0; const int* sh_g1;
-  int H, G, S, nhyp, arows;
+  int H, G, S, nhyp;
   int hyp_begin[MAXH + 1];
   int hyp_half[MAXH];
   int hyp_A0[MAXH], hyp_nA[MAXH], hyp_B0[MAXH], hyp_nB[MAXH];
@@ -703,20 +702,13 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
     k_wcorr<WC_KT><<<(unsigned)std::min<int64_t>(ctas_c, (int64_t)3 * sms), WC_TPB, smem_c, s>>>(wc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     st->launches++;
-    if (getenv("BFL_WSPLIT_DEBUG")) {
-      e = cudaStreamSynchronize(s);
-      fprintf(stderr, "[wsplit] k_wcorr B=%d nk=%lld rows=%d nj=%d tab=%d n=%d,%d,%d|%d,%d,%d smem=%zu grid=%lld -> %s\n", Bc, (long long)nk,
-              pv.wc_rows, pv.wc_nj, pv.wc_tab_len, wc.n[0][0], wc.n[0][1], wc.n[0][2], wc.n[1][0], wc.n[1][1], wc.n[1][2], smem_c,
-              (long long)std::min<int64_t>(ctas_c, (int64_t)3 * sms), cudaGetErrorString(e));
-      if (e != cudaSuccess) return e;
-    }
 
     WSolveArgs ws;
     ws.Y = Yw; ws.BK = wc.BK; ws.nk = nk; ws.N = a.N; ws.k0 = a.k0;
     ws.ki0 = (int64_t)b0 * nk; ws.part_stride = (int64_t)a.B * nk;
     ws.total_wtiles = (ws.BK + 31) / 32;
     ws.shrow = pv.wc_shrow; ws.lp = a.lp; ws.lw = a.lw; ws.idxA = a.idxA; ws.sh_g0 = a.sh_g0; ws.sh_g1 = a.sh_g1;
-    ws.H = a.W / 2; ws.G = a.G; ws.S = a.S; ws.nhyp = a.nhyp; ws.arows = 0;
+    ws.H = a.W / 2; ws.G = a.G; ws.S = a.S; ws.nhyp = a.nhyp;
     for (int h = 0; h <= a.nhyp; h++) ws.hyp_begin[h] = a.hyp_begin[h];
     for (int h = 0; h < a.nhyp; h++) {
       ws.hyp_half[h] = a.hyp_half[h];
@@ -736,12 +728,6 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
     }
     if (e != cudaSuccess) return e;
     st->launches++;
-    if (getenv("BFL_WSPLIT_DEBUG")) {
-      e = cudaStreamSynchronize(s);
-      fprintf(stderr, "[wsplit] k_wsolve P=%d G=%d S=%d nhyp=%d arows=%d smem=%zu tiles=%lld -> %s\n", pv.P, ws.G, ws.S, ws.nhyp, ws.arows,
-              smem_s, (long long)ws.total_wtiles, cudaGetErrorString(e));
-      if (e != cudaSuccess) return e;
-    }
   }
   return cudaSuccess;
 }
