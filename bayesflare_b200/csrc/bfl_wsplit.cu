@@ -539,10 +539,60 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
           myAB[(2 * i + 2) * TPB] = V1[P];
           myAB[(2 * i + 3) * TPB] = V1[P + 1];
         }
+        if constexpr (LIN) {
+          // Software pipeline over the B shapes: the NEXT shape's solve (a serial chain of ~45 instructions) sits in
+          // the same basic block as this shape's first five templates, so ptxas interleaves it with their chains.
+          // `half` is hoisted out of the loop for the same reason (a branch ends the block).
+          auto b_loop = [&](auto half_tag) {
+            double Vc[NV];
+            {
+              double F[NV];
+              take(nsh++, F);
+              solve(F, Vc);
+            }
+            for (int j = 0; j < nB; j++) {
+              double Fn[NV], Vn[NV];
+              if (j + 1 < nB) {
+                take(nsh++, Fn);
+              } else {
+#pragma unroll
+                for (int q = 0; q < NV; q++) Fn[q] = 0.0;
+              }
+              const double* cw = sC + (size_t)(B0 + j) * NA;
+              const int* gi = sGi + (size_t)(B0 + j) * NA;
+              auto five = [&](auto itag) {
+                constexpr int I0 = decltype(itag)::value;
+                double sv[5], rv[5];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                  double d = 0.0;
+#pragma unroll
+                  for (int q = 0; q < P; q++) d = fma(yA[I0 + c][q], Vc[q], d);
+                  sv[c] = fma(-2.0, d, Vc[P] + myAB[(2 * (I0 + c)) * TPB]);
+                  rv[c] = Vc[P + 1] + myAB[(2 * (I0 + c) + 1) * TPB];
+                }
+#pragma unroll
+                for (int c = 0; c < 5; c++) lin_term(half_tag, sv[c], rv[c], cw[I0 + c]);   // weight 0: pair excluded
+              };
+              solve(Fn, Vn);
+              five(std::integral_constant<int, 0>{});
+              bool any = false;
+#pragma unroll
+              for (int c = 5; c < NA; c++) any = any || gi[c] >= 0;
+              if (any) five(std::integral_constant<int, 5>{});   // (warp-uniform)
+#pragma unroll
+              for (int q = 0; q < NV; q++) Vc[q] = Vn[q];
+            }
+          };
+          static_assert(NA == 10, "the grouping is written for ten A shapes");
+          if (nB > 0) {
+            if (half) b_loop(std::true_type{});
+            else b_loop(std::false_type{});
+          }
+        } else {
         for (int j = 0; j < nB; j++) {
           double F[NV], V[NV];
-          if constexpr (LIN) take(nsh++, F);
-          else load_shape(B0 + j, F);
+          load_shape(B0 + j, F);
           solve(F, V);
           const double* cw = sC + (size_t)(B0 + j) * NA;
           const int* gi = sGi + (size_t)(B0 + j) * NA;
@@ -564,9 +614,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
             }
             many(ktag, sv, rv, cw + I0, gi + I0);
           };
-          static_assert(NA == 10, "the grouping below is written for ten A shapes");
           group(std::integral_constant<int, 0>{}, std::integral_constant<int, 5>{});
           group(std::integral_constant<int, 5>{}, std::integral_constant<int, 5>{});
+        }
         }
       } else {
         // dense hypothesis: one template per shape, two shapes at a time
