@@ -42,6 +42,8 @@ struct WCorrArgs {
   int tab_len, nj;
   double* Y;                               // [rows][BK]
   int64_t BK;
+  unsigned long long* tile_counter;        // dynamic warp tiles (as k_corr_shapes): the last warp to leave re-arms both
+  unsigned long long* done_counter;
 };
 
 constexpr int WC_TPB = 128, WC_KT = 4;
@@ -93,7 +95,17 @@ __global__ void __launch_bounds__(WC_TPB, 3) k_wcorr(const WCorrArgs a) {
   }
   __syncthreads();
   const int64_t nk = a.k1 - a.k0;
-  for (int64_t wt = (int64_t)blockIdx.x * (WC_TPB / 32) + warp; wt < a.total_wtiles; wt += (int64_t)gridDim.x * (WC_TPB / 32)) {
+  for (;;) {
+    long long wt = 0;
+    if (lane == 0) wt = (long long)atomicAdd(a.tile_counter, 1ULL);
+    wt = __shfl_sync(0xffffffffu, wt, 0);
+    if (wt >= a.total_wtiles) {
+      if (lane == 0 && atomicAdd(a.done_counter, 1ULL) == (unsigned long long)gridDim.x * (WC_TPB / 32) - 1ULL) {
+        *a.tile_counter = 0ULL;
+        *a.done_counter = 0ULL;
+      }
+      break;
+    }
     const int tile = (int)(wt % a.tiles_per_curve);
     const int b = (int)(wt / a.tiles_per_curve);
     const int64_t kbase = a.k0 + (int64_t)tile * TKW;
@@ -735,8 +747,11 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
   const size_t smem_c = wcorr_smem(pv), smem_s = wsolve_smem(pv);
   cudaError_t e = cudaFuncSetAttribute(k_wcorr<WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
   if (e != cudaSuccess) return e;
-  for (int b0 = 0; b0 < a.B; b0 += chunk_curves) {
-    const int Bc = std::min(chunk_curves, a.B - b0);
+  // chunks of equal size (a short last chunk would leave the correlation kernel's last round of tiles half empty)
+  const int nchunks = (a.B + chunk_curves - 1) / chunk_curves;
+  const int chunk = (a.B + nchunks - 1) / nchunks;
+  for (int b0 = 0; b0 < a.B; b0 += chunk) {
+    const int Bc = std::min(chunk, a.B - b0);
     WCorrArgs wc;
     wc.dw = a.dw + (size_t)b0 * a.seglen; wc.uu = a.uu + (size_t)b0 * a.seglen;
     wc.seglen = a.seglen; wc.N = a.N; wc.seg0 = a.seg0; wc.k0 = a.k0; wc.k1 = a.k1;
@@ -748,6 +763,7 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
       for (int j = 0; j < 3; j++) wc.n[i][j] = pv.wc_n[i][j];
     wc.tab_len = pv.wc_tab_len; wc.nj = pv.wc_nj;
     wc.Y = Yw; wc.BK = (int64_t)Bc * nk;
+    wc.tile_counter = counters + 1; wc.done_counter = counters + 3;
     const int64_t ctas_c = (wc.total_wtiles + WC_TPB / 32 - 1) / (WC_TPB / 32);
     k_wcorr<WC_KT><<<(unsigned)std::min<int64_t>(ctas_c, (int64_t)3 * sms), WC_TPB, smem_c, s>>>(wc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
