@@ -25,7 +25,7 @@
 //
 //  * WEIGHTED path (interior samples of curves with per-sample variance, i.e. real light curves
 //    with flux errors): the same integral with a per-sample P x P Cholesky in the orthonormal
-//    basis.  Default window length and grid: the split form of bfl_wsplit.cu (k_wcorr + k_wsolve);
+//    basis.  Window lengths 21 / 33 / 55 and the default grid: the split form of bfl_wsplit.cu (k_wcorr + k_wsolve);
 //    otherwise k_window_wsep (separable, one kernel) or k_window_weighted (dense / full output).
 //
 //  * GENERAL path (first/last W/2 samples where the reference truncates the window,

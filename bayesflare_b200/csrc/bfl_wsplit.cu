@@ -49,8 +49,8 @@ struct WCorrArgs {
 constexpr int WC_TPB = 128, WC_KT = 4;
 
 // z[j] = sum over taps T0 .. T0+NT-1 of t[w - T0] * win[w + j]; `t` points at the vector's first stored tap
-template <int T0, int NT, int KT>
-__device__ __forceinline__ void corr_taps(const double* __restrict__ t, const double (&win)[55 + KT - 1], double (&z)[KT]) {
+template <int T0, int NT, int KT, int WL>
+__device__ __forceinline__ void corr_taps(const double* __restrict__ t, const double (&win)[WL], double (&z)[KT]) {
   constexpr int NPAIR = NT / 2;
   double acc[KT][2];
 #pragma unroll
@@ -75,11 +75,12 @@ __device__ __forceinline__ void corr_taps(const double* __restrict__ t, const do
   }
 }
 
-// W = 55 only (the reference's default bglen; other lengths keep k_window_wsep / k_window_weighted)
-template <int KT>
+// W is a compile-time window length: instantiated for 21, 33 and 55 (the reference's default and the shorter lengths its
+// scripts use); other lengths keep k_window_wsep / k_window_weighted
+template <int W, int KT>
 __global__ void __launch_bounds__(WC_TPB, 3) k_wcorr(const WCorrArgs a) {
   extern __shared__ double smem[];
-  constexpr int W = 55, H = W / 2, TKW = 32 * KT;
+  constexpr int H = W / 2, TKW = 32 * KT;
   constexpr int T0H = H & ~1, NTL = H + 1, NTH = W - T0H;
   constexpr int wstride = (TKW + 2 * H + 2) & ~1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,19 +146,19 @@ __global__ void __launch_bounds__(WC_TPB, 3) k_wcorr(const WCorrArgs a) {
 #pragma unroll 1
       for (int i = 0; i < a.n[st][0]; i++, jb++) {
         double y[KT];
-        corr_taps<0, W, KT>(stab + soff[jb], win, y);
+        corr_taps<0, W, KT, W + KT - 1>(stab + soff[jb], win, y);
         put(jb, y);
       }
 #pragma unroll 1
       for (int i = 0; i < a.n[st][1]; i++, jb++) {
         double y[KT];
-        corr_taps<0, NTL, KT>(stab + soff[jb], win, y);
+        corr_taps<0, NTL, KT, W + KT - 1>(stab + soff[jb], win, y);
         put(jb, y);
       }
 #pragma unroll 1
       for (int i = 0; i < a.n[st][2]; i++, jb++) {
         double y[KT];
-        corr_taps<T0H, NTH, KT>(stab + soff[jb], win, y);
+        corr_taps<T0H, NTH, KT, W + KT - 1>(stab + soff[jb], win, y);
         put(jb, y);
       }
     }
@@ -692,10 +693,10 @@ __global__ void __launch_bounds__(TPB, MINB) k_wsolve(const WSolveArgs a) {
 // --------------------------------------------------------------------------------------
 // host side
 // --------------------------------------------------------------------------------------
-bool wsplit_window_supported(int W) { return W == 55; }
+bool wsplit_window_supported(int W) { return W == 21 || W == 33 || W == 55; }
 
 static size_t wcorr_smem(const PlanView& pv) {
-  constexpr int wstride = (32 * WC_KT + 2 * 27 + 2) & ~1;
+  const int wstride = (32 * WC_KT + 2 * (pv.W / 2) + 2) & ~1;
   return sizeof(double) * ((size_t)(WC_TPB / 32) * 2 * wstride + (size_t)pv.wc_tab_len) + sizeof(int) * (size_t)(2 * pv.wc_nj + 2);
 }
 
@@ -709,7 +710,7 @@ static size_t wsolve_smem(const PlanView& pv) {
 bool wsplit_fits(const PlanView& pv) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("BFL_NO_WSPLIT"); off = (e && atoi(e)) ? 1 : 0; }
-  if (off || pv.wc_tab == nullptr || pv.W != 55 || pv.P < 1 || pv.P > 6 || (pv.wc_tab_len % 2) != 0) return false;
+  if (off || pv.wc_tab == nullptr || !wsplit_window_supported(pv.W) || pv.P < 1 || pv.P > 6 || (pv.wc_tab_len % 2) != 0) return false;
   for (int h = 0; h < pv.nhyp; h++)
     if (pv.hyp_nA[h] > WS_NA) return false;         // the A shapes' y vectors live in registers
   return wcorr_smem(pv) <= 72 * 1024 && wsolve_smem(pv) <= 112 * 1024;
@@ -745,7 +746,13 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
                                  LaunchStats* st) {
   const int64_t nk = a.k1 - a.k0;
   const size_t smem_c = wcorr_smem(pv), smem_s = wsolve_smem(pv);
-  cudaError_t e = cudaFuncSetAttribute(k_wcorr<WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+  cudaError_t e = cudaSuccess;
+  switch (pv.W) {
+    case 21: e = cudaFuncSetAttribute(k_wcorr<21, WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c); break;
+    case 33: e = cudaFuncSetAttribute(k_wcorr<33, WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c); break;
+    case 55: e = cudaFuncSetAttribute(k_wcorr<55, WC_KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c); break;
+    default: return cudaErrorInvalidValue;
+  }
   if (e != cudaSuccess) return e;
   // chunks of equal size (a short last chunk would leave the correlation kernel's last round of tiles half empty)
   const int nchunks = (a.B + chunk_curves - 1) / chunk_curves;
@@ -765,7 +772,10 @@ cudaError_t launch_window_wsplit(const PlanView& pv, const WsepArgs& a, double* 
     wc.Y = Yw; wc.BK = (int64_t)Bc * nk;
     wc.tile_counter = counters + 1; wc.done_counter = counters + 3;
     const int64_t ctas_c = (wc.total_wtiles + WC_TPB / 32 - 1) / (WC_TPB / 32);
-    k_wcorr<WC_KT><<<(unsigned)std::min<int64_t>(ctas_c, (int64_t)3 * sms), WC_TPB, smem_c, s>>>(wc);
+    const unsigned grid_c = (unsigned)std::min<int64_t>(ctas_c, (int64_t)3 * sms);
+    if (pv.W == 21) k_wcorr<21, WC_KT><<<grid_c, WC_TPB, smem_c, s>>>(wc);
+    else if (pv.W == 33) k_wcorr<33, WC_KT><<<grid_c, WC_TPB, smem_c, s>>>(wc);
+    else k_wcorr<55, WC_KT><<<grid_c, WC_TPB, smem_c, s>>>(wc);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     st->launches++;
 

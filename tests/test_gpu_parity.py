@@ -461,10 +461,11 @@ def _varying_cle_case(N, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bglen,bgorder", [(55, 4), (55, 2), (55, 5), (55, 0), (35, 3)])
+@pytest.mark.parametrize("bglen,bgorder", [(55, 4), (55, 2), (55, 5), (55, 0), (35, 3), (33, 3), (21, 1)])
 def test_weighted_detector_vs_oracle(bglen, bgorder):
-    """default detector on a curve with per-sample errors, edges included; bglen 35 has no separable
-    form (the plain weighted kernel runs), bgorder 0..5 instantiate every polynomial size"""
+    """default detector on a curve with per-sample errors, edges included; bglen 21 / 33 / 55 take the split form
+    (k_wcorr + k_wsolve), bglen 35 has no separable form (the plain weighted kernel runs), bgorder 0..5 instantiate
+    every polynomial size"""
     ts, clc, cle = _varying_cle_case(900, 100 + bgorder)
     kw = dict(bglen=bglen, bgorder=bgorder, noiseestmethod="tailveto", ignoreedges=False)
     if bglen != 55:
