@@ -13,9 +13,11 @@
 //   k_wcorr  : the correlations, data window of KT + W - 1 samples in registers, vectors broadcast from shared
 //              memory as 128-bit loads, taps unrolled at compile time per support class (whole window / rise half /
 //              decay half: a flare shape touches only its half)            -> Yw[row][sample]
-//   k_wsolve : per sample Cholesky + L^-1, per shape solve, per template term, log-sum-exp.  A sample belongs to a
-//              PAIR of lanes (l, l + 16) that share its shared-memory slice of A-shape results and split the shapes,
-//              so 16 warps per SM fit; the next group's sums are prefetched while the current one is reduced.
+//   k_wsolve : one sample per thread -- Cholesky + L^-1, per shape solve, per template term, the grid sums in the
+//              linear domain (log-domain redo for samples with a flare), the hypotheses folded into the log odds.
+//              The y vectors of the A shapes stay in registers; the shapes' sums are prefetched four shapes ahead
+//              with cp.async.  About 1 KB of state per sample caps the SM at 8 warps, so the kernel lives on
+//              instruction-level parallelism: five templates per basic block, no run-time branch inside a block.
 // Yw makes one round trip through HBM (8 (P(P+3)/2 + (P+2) S') bytes per sample each way, S' non-empty shapes).
 // The one-kernel form k_window_wsep sits at 45 % of the FP64 pipe with 8 warps per SM and a tap loop of 113
 // instructions for 64 DFMAs; a two-threads-per-sample variant of it was measured no faster (round 2).
